@@ -1,0 +1,725 @@
+// C-ABI layer: context, device buffers, launch configuration.  See include/fd_b200.h for the contract.
+// There is deliberately no CPU implementation behind any entry point.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fd_b200.h"
+#include "fd_kernels.cuh"
+
+using namespace fdb;
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct fd_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    FrameView fv = {};
+    bool frames_bound = false;
+    DevBuf owned_frames;
+
+    DevBuf lut;       // 65536 B
+    DevBuf segs;      // OffsetSeg table
+    int n_seg = 0;
+    uint32_t seg_count_covered = 0;
+
+    DevBuf keys, keys_scratch, counts, flags, cells;
+    uint32_t cand_capacity = 0;
+    bool have_candidates = false, candidates_sorted = false;
+
+    DevBuf kp, kp_counts;
+    int kp_capacity = 0;
+    bool have_keypoints = false;
+
+    DevBuf user_kp, user_counts;
+    int user_capacity = 0;
+
+    DevBuf desc;
+    int desc_capacity = 0;     // slots per frame of the described set
+    bool desc_from_user = false;
+    bool have_desc = false;
+
+    DevBuf mask_bits, mask_rowbase, mask_prefix, existing_xy, existing_counts;
+    int existing_capacity = 0;
+    bool have_existing = false;
+
+    float *resp_map = nullptr;
+    uint8_t *score_map = nullptr;
+
+    DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted;
+    float *lsd_norm_p = nullptr, *lsd_angle_p = nullptr;
+    int32_t *lsd_sorted_p = nullptr, *lsd_nvalid_p = nullptr;
+    bool have_lsd = false, lsd_sorted_valid = false;
+};
+
+namespace {
+
+fd_status fail(fd_context *ctx, fd_status st, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return st;
+}
+
+#define FD_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? FD_ERR_OUT_OF_MEMORY : FD_ERR_CUDA, \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+        }                                                                                           \
+    } while (0)
+
+#define FD_TRY(expr)                      \
+    do {                                  \
+        fd_status s__ = (expr);           \
+        if (s__ != FD_OK) return s__;     \
+    } while (0)
+
+fd_status reserve(fd_context *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.bytes && b.ptr != nullptr) return FD_OK;
+    if (b.ptr != nullptr) {
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FD_CUDA(ctx, cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    if (bytes == 0) bytes = 16;
+    FD_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
+    b.bytes = bytes;
+    return FD_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+
+// Longest circular run of set bits in a 16-bit ring mask (feature_point_fast_detector.cpp:55-78).
+std::vector<uint8_t> build_run_lut() {
+    std::vector<uint8_t> lut(65536);
+    for (uint32_t m = 0; m < 65536; ++m) {
+        if (m == 0xFFFFu) {
+            lut[m] = 16;
+            continue;
+        }
+        int best = 0, run = 0;
+        for (int i = 0; i < 32; ++i) {
+            if ((m >> (i & 15)) & 1u) {
+                ++run;
+                best = std::max(best, run);
+            } else {
+                run = 0;
+            }
+        }
+        lut[m] = uint8_t(std::min(best, 16));
+    }
+    return lut;
+}
+
+// Piecewise-linear description of the reference's running offset (fast.cpp:85,93):
+//   offset_0 = 1e-5f;  offset_{k+1} = fl(offset_k + 1e-5f).
+// Inside one binade every add rounds to the same number of ulps, so the float's BIT PATTERN advances by a
+// constant per step; a new piece starts wherever that constant changes.  Built by running the same float
+// loop once (volatile keeps the host compiler from using wider intermediates).
+std::vector<OffsetSeg> build_offset_table(uint32_t count) {
+    std::vector<OffsetSeg> segs;
+    volatile float offset = 1e-5f;
+    const volatile float inc = 1e-5f;
+    auto bits = [](float f) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    };
+    uint32_t prev_bits = bits(offset);
+    segs.push_back({0u, prev_bits, 0u});
+    bool step_known = false;
+    for (uint32_t k = 1; k < count; ++k) {
+        offset = offset + inc;
+        const uint32_t b = bits(offset);
+        const uint32_t step = b - prev_bits;
+        OffsetSeg &cur = segs.back();
+        if (!step_known) {
+            cur.step = step;
+            step_known = true;
+        } else if (step != cur.step) {
+            // the value at k is no longer on the current line: open a new piece starting AT k
+            segs.push_back({k, b, 0u});
+            step_known = false;
+        }
+        prev_bits = b;
+    }
+    segs.push_back({0xFFFFFFFFu, 0u, 0u});  // sentinel
+    return segs;
+}
+
+fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
+    if (ctx->lut.ptr == nullptr) {
+        const std::vector<uint8_t> lut = build_run_lut();
+        FD_TRY(reserve(ctx, ctx->lut, 65536));
+        FD_CUDA(ctx, cudaMemcpyAsync(ctx->lut.ptr, lut.data(), 65536, cudaMemcpyHostToDevice, ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (count > ctx->seg_count_covered || ctx->segs.ptr == nullptr) {
+        const uint32_t want = std::max<uint32_t>(count, 1u << 20);
+        const std::vector<OffsetSeg> segs = build_offset_table(want);
+        FD_TRY(reserve(ctx, ctx->segs, segs.size() * sizeof(OffsetSeg)));
+        FD_CUDA(ctx, cudaMemcpyAsync(ctx->segs.ptr, segs.data(), segs.size() * sizeof(OffsetSeg), cudaMemcpyHostToDevice, ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->n_seg = int(segs.size()) - 1;
+        ctx->seg_count_covered = want;
+    }
+    return FD_OK;
+}
+
+// Split the interior rows into bands so that every resident warp gets several work items.
+void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_frames, int warps_per_cta, int ctas_per_sm, int min_band,
+                int &band_rows, int &n_bands, int64_t &n_items, int &grid) {
+    grid = ctx->sm_count * ctas_per_sm;
+    const int64_t total_warps = int64_t(grid) * warps_per_cta;
+    const int64_t base_items = int64_t(n_frames) * n_strips;
+    int64_t want_bands = (8 * total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
+    want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, std::max(1, interior_rows / min_band)));
+    band_rows = int((interior_rows + want_bands - 1) / want_bands);
+    band_rows = std::max(band_rows, 1);
+    n_bands = (interior_rows + band_rows - 1) / band_rows;
+    n_items = base_items * n_bands;
+    const int64_t ctas_needed = (n_items + warps_per_cta - 1) / warps_per_cta;
+    grid = int(std::max<int64_t>(1, std::min<int64_t>(grid, ctas_needed)));
+}
+
+fd_status require_frames(fd_context *ctx) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->frames_bound) return fail(ctx, FD_ERR_NOT_READY, "no frames bound: call fd_upload_frames or fd_bind_device_frames first");
+    return FD_OK;
+}
+
+fd_status check_params(fd_context *ctx, const fd_detect_params *p) {
+    if (!p) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "params is null");
+    if (p->kind < FD_HARRIS || p->kind > FD_FAST) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "unknown detector kind");
+    if (p->fast_min_pixel_diff < 0 || p->fast_min_pixel_diff > 255) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fast_min_pixel_diff out of [0,255]");
+    if (p->reserved != 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "reserved must be 0");
+    return FD_OK;
+}
+
+fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_capacity) {
+    FD_TRY(require_frames(ctx));
+    FD_TRY(check_params(ctx, p));
+    if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not implemented in this build");
+    const FrameView &fv = ctx->fv;
+    const int64_t px = int64_t(fv.rows) * fv.cols;
+    if (px >= (int64_t(1) << 31)) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame too large");
+    const uint32_t cap = cand_capacity > 0 ? uint32_t(std::min<int64_t>(cand_capacity, px)) : uint32_t(px);
+    ctx->cand_capacity = cap;
+    FD_TRY(reserve(ctx, ctx->keys, size_t(fv.n_frames) * cap * 8));
+    FD_TRY(reserve(ctx, ctx->counts, size_t(fv.n_frames) * 4));
+    FD_TRY(reserve(ctx, ctx->flags, 16));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->counts.ptr, 0, size_t(fv.n_frames) * 4, ctx->stream));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->flags.ptr, 0, 16, ctx->stream));
+    ctx->have_candidates = false;
+    ctx->candidates_sorted = false;
+    ctx->have_keypoints = false;
+
+    if (p->kind == FD_FAST) {
+        if (ctx->score_map) FD_CUDA(ctx, cudaMemsetAsync(ctx->score_map, 0, size_t(fv.n_frames) * px, ctx->stream));
+        if (fv.rows >= 7 && fv.cols >= 7) {
+            const uint32_t interior = uint32_t(fv.rows - 6) * uint32_t(fv.cols - 6);
+            FD_TRY(ensure_fast_tables(ctx, interior));
+            FastArgs a = {};
+            a.fv = fv;
+            a.diff = p->fast_min_pixel_diff;
+            a.thr = p->min_valid_response;
+            a.lut = static_cast<const uint8_t *>(ctx->lut.ptr);
+            a.segs = static_cast<const OffsetSeg *>(ctx->segs.ptr);
+            a.n_seg = ctx->n_seg;
+            a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
+            a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
+            a.cand_capacity = cap;
+            a.score_map = ctx->score_map;
+            a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
+            a.n_strips = (fv.cols + 127) / 128;
+            int grid;
+            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, 2, 16, a.band_rows, a.n_bands, a.n_items, grid);
+            FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
+            ++ctx->launches;
+        }
+    } else {
+        if (ctx->resp_map) FD_CUDA(ctx, cudaMemsetAsync(ctx->resp_map, 0, size_t(fv.n_frames) * px * 4, ctx->stream));
+        if (fv.rows >= 5 && fv.cols >= 5) {
+            CornerArgs a = {};
+            a.fv = fv;
+            a.kind = p->kind;
+            a.thr = p->min_valid_response;
+            a.alpha = p->harris_alpha;
+            volatile float nine = 9.0f;
+            volatile float inv = 1.0f / nine;                 // harris.cpp:71
+            volatile float inv2 = inv * inv;                  // harris.cpp:72
+            a.inv_cnt = inv;
+            a.inv_cnt2 = inv2;
+            a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
+            a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
+            a.cand_capacity = cap;
+            a.response_map = ctx->resp_map;
+            a.n_strips = (fv.cols - 4 + CORNER_STRIP_OUT - 1) / CORNER_STRIP_OUT;
+            int grid;
+            plan_bands(ctx, fv.rows - 4, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, a.band_rows, a.n_bands, a.n_items, grid);
+            FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
+            ++ctx->launches;
+        }
+    }
+    ctx->have_candidates = true;
+    return FD_OK;
+}
+
+fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
+    const FrameView &fv = ctx->fv;
+    const int kp_cap = int(std::max<uint32_t>(1u, std::min<uint32_t>(p->needed_feature_num, 1u << 20)));
+    ctx->kp_capacity = kp_cap;
+    FD_TRY(reserve(ctx, ctx->kp, size_t(fv.n_frames) * kp_cap * sizeof(float4)));
+    FD_TRY(reserve(ctx, ctx->kp_counts, size_t(fv.n_frames) * 4));
+    SelectArgs a = {};
+    a.rows = fv.rows;
+    a.cols = fv.cols;
+    a.n_frames = fv.n_frames;
+    a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
+    a.cand_scratch = nullptr;
+    a.cand_counts = static_cast<const uint32_t *>(ctx->counts.ptr);
+    a.cand_capacity = ctx->cand_capacity;
+    a.min_distance = p->min_feature_distance;
+    a.needed = p->needed_feature_num;
+    a.existing_counts = ctx->have_existing ? static_cast<const int32_t *>(ctx->existing_counts.ptr) : nullptr;
+    a.keypoints = static_cast<float4 *>(ctx->kp.ptr);
+    a.kp_counts = static_cast<int32_t *>(ctx->kp_counts.ptr);
+    a.kp_capacity = kp_cap;
+    const int cell = std::max(p->min_feature_distance, 0) + 1;
+    a.cells_x = (fv.cols + cell - 1) / cell;
+    a.cells_y = (fv.rows + cell - 1) / cell;
+    const size_t cell_bytes = size_t(a.cells_x) * a.cells_y * 4;
+    a.cells_in_smem = cell_bytes <= 64 * 1024;
+    if (!a.cells_in_smem) {
+        FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
+        a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
+    }
+    int sort_cap = 1024;
+    while (uint32_t(sort_cap) < ctx->cand_capacity && sort_cap < 16384) sort_cap <<= 1;
+    a.smem_sort_capacity = sort_cap;
+    a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
+    FD_CUDA(ctx, launch_select(a, ctx->stream));
+    ++ctx->launches;
+    ctx->candidates_sorted = true;
+    ctx->have_keypoints = true;
+    return FD_OK;
+}
+
+fd_status check_overflow(fd_context *ctx) {
+    if (ctx->flags.ptr == nullptr) return FD_OK;
+    uint32_t flag = 0;
+    FD_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag != 0) return fail(ctx, FD_ERR_CAPACITY, "a frame produced more candidates than cand_capacity; raise it and run again");
+    return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fd_version(void) { return "feature_detector_b200 0.1 (sm_100a)"; }
+
+fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
+    if (!out_ctx) return FD_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return FD_ERR_NO_DEVICE;
+    if (device_ordinal < 0 || device_ordinal >= n) return FD_ERR_INVALID_ARGUMENT;
+    fd_context *ctx = new (std::nothrow) fd_context();
+    if (!ctx) return FD_ERR_OUT_OF_MEMORY;
+    ctx->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return FD_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    *out_ctx = ctx;
+    return FD_OK;
+}
+
+fd_status fd_destroy(fd_context *ctx) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->kp,
+                      &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted})
+        release(*b);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return FD_OK;
+}
+
+const char *fd_last_error(const fd_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+fd_status fd_set_stream(fd_context *ctx, void *cuda_stream) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return FD_OK;
+}
+
+fd_status fd_sync(fd_context *ctx) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->have_candidates) return check_overflow(ctx);
+    return FD_OK;
+}
+
+uint64_t fd_launch_count(const fd_context *ctx) { return ctx ? ctx->launches : 0; }
+
+fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames) {
+    if (!ctx || !host_frames || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_upload_frames: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t pitch = (int64_t(cols) + 15) / 16 * 16;
+    const int64_t stride = pitch * rows;
+    FD_TRY(reserve(ctx, ctx->owned_frames, size_t(stride) * n_frames));
+    FD_CUDA(ctx, cudaMemcpy2DAsync(ctx->owned_frames.ptr, size_t(pitch), host_frames, size_t(cols), size_t(cols), size_t(rows) * n_frames,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, pitch, stride, n_frames, int(pitch / 4)};
+    ctx->frames_bound = true;
+    ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
+    return FD_OK;
+}
+
+fd_status fd_bind_device_frames(fd_context *ctx, const uint8_t *dev_frames, int rows, int cols, int64_t pitch, int64_t frame_stride, int n_frames) {
+    if (!ctx || !dev_frames || rows <= 0 || cols <= 0 || n_frames <= 0 || pitch < cols || frame_stride < pitch * rows)
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_bind_device_frames: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool aligned = (reinterpret_cast<uintptr_t>(dev_frames) % 4 == 0) && (pitch % 4 == 0) && (frame_stride % 4 == 0);
+    if (aligned) {
+        ctx->fv = FrameView{dev_frames, rows, cols, pitch, frame_stride, n_frames, int(pitch / 4)};
+    } else {
+        // re-pitch so that rows can be read as aligned words
+        const int64_t np = (int64_t(cols) + 15) / 16 * 16;
+        const int64_t ns = np * rows;
+        FD_TRY(reserve(ctx, ctx->owned_frames, size_t(ns) * n_frames));
+        for (int f = 0; f < n_frames; ++f)
+            FD_CUDA(ctx, cudaMemcpy2DAsync(static_cast<uint8_t *>(ctx->owned_frames.ptr) + ns * f, size_t(np), dev_frames + frame_stride * f,
+                                           size_t(pitch), size_t(cols), size_t(rows), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, np, ns, n_frames, int(np / 4)};
+    }
+    ctx->frames_bound = true;
+    ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
+    return FD_OK;
+}
+
+fd_status fd_set_existing_features(fd_context *ctx, const float *host_xy, const int32_t *host_counts, int capacity, int n_frames) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (n_frames == 0) {
+        ctx->have_existing = false;
+        return FD_OK;
+    }
+    (void)host_xy; (void)host_counts; (void)capacity;
+    return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not implemented in this build");
+}
+
+fd_status fd_set_dense_outputs(fd_context *ctx, float *dev_response_map, uint8_t *dev_fast_score_map) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    ctx->resp_map = dev_response_map;
+    ctx->score_map = dev_fast_score_map;
+    return FD_OK;
+}
+
+fd_status fd_compute_candidates(fd_context *ctx, const fd_detect_params *params, int cand_capacity) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_candidates(ctx, params, cand_capacity);
+}
+
+fd_status fd_detect(fd_context *ctx, const fd_detect_params *params, int cand_capacity) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(run_candidates(ctx, params, cand_capacity));
+    return run_select(ctx, params);
+}
+
+fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts) {
+    if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
+    FD_CUDA(ctx, cudaMemcpyAsync(host_counts, ctx->counts.ptr, size_t(ctx->fv.n_frames) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out) {
+    if (!ctx || !n_out) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
+    if (frame < 0 || frame >= ctx->fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame out of range");
+    FD_TRY(check_overflow(ctx));
+    uint32_t n = 0;
+    FD_CUDA(ctx, cudaMemcpyAsync(&n, static_cast<uint32_t *>(ctx->counts.ptr) + frame, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    if (host_cand == nullptr) return FD_OK;
+    if (int64_t(n) > capacity) return fail(ctx, FD_ERR_CAPACITY, "host candidate buffer too small");
+    std::vector<uint64_t> keys(n);
+    FD_CUDA(ctx, cudaMemcpyAsync(keys.data(), static_cast<uint64_t *>(ctx->keys.ptr) + int64_t(frame) * ctx->cand_capacity, size_t(n) * 8,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->candidates_sorted) std::sort(keys.begin(), keys.end());  // presentation order only; selection never takes this path
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t raster = cand_key_raster(keys[i]);
+        host_cand[i].response = cand_key_response(keys[i]);
+        host_cand[i].x = int32_t(raster % uint32_t(ctx->fv.cols));
+        host_cand[i].y = int32_t(raster / uint32_t(ctx->fv.cols));
+    }
+    return FD_OK;
+}
+
+fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *host_counts, int kp_capacity) {
+    if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
+    FD_TRY(check_overflow(ctx));
+    const int nf = ctx->fv.n_frames;
+    FD_CUDA(ctx, cudaMemcpyAsync(host_counts, ctx->kp_counts.ptr, size_t(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_kp != nullptr) {
+        static_assert(sizeof(fd_keypoint) == sizeof(float4), "fd_keypoint layout");
+        if (kp_capacity == ctx->kp_capacity) {
+            FD_CUDA(ctx, cudaMemcpyAsync(host_kp, ctx->kp.ptr, size_t(nf) * kp_capacity * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            const int w = std::min(kp_capacity, ctx->kp_capacity);
+            FD_CUDA(ctx, cudaMemcpy2DAsync(host_kp, size_t(kp_capacity) * sizeof(float4), ctx->kp.ptr, size_t(ctx->kp_capacity) * sizeof(float4),
+                                           size_t(w) * sizeof(float4), size_t(nf), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_kp != nullptr)
+        for (int f = 0; f < nf; ++f)
+            if (host_counts[f] > kp_capacity) return fail(ctx, FD_ERR_CAPACITY, "host keypoint buffer too small");
+    return FD_OK;
+}
+
+fd_status fd_device_keypoints(fd_context *ctx, const fd_keypoint **dev_kp, const int32_t **dev_counts, int *kp_capacity) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
+    if (dev_kp) *dev_kp = static_cast<const fd_keypoint *>(ctx->kp.ptr);
+    if (dev_counts) *dev_counts = static_cast<const int32_t *>(ctx->kp_counts.ptr);
+    if (kp_capacity) *kp_capacity = ctx->kp_capacity;
+    return FD_OK;
+}
+
+fd_status fd_sparsify(const float *host_xy, int n, int image_rows, int image_cols, int grid_rows, int grid_cols, uint8_t status_need_filter,
+                      uint8_t status_after_filter, uint8_t *status) {
+    if (n < 0 || (n > 0 && (!host_xy || !status)) || grid_rows < 2 || grid_cols < 2) return FD_ERR_INVALID_ARGUMENT;
+    const int row_div = image_rows / (grid_rows - 1), col_div = image_cols / (grid_cols - 1);  // integer division, feature_point_detector.cpp:34-35
+    const float row_step = float(row_div), col_step = float(col_div);
+    std::vector<uint8_t> free_cell(size_t(grid_rows) * grid_cols, 1);                          // :36
+    for (int i = 0; i < n; ++i) {
+        const int row = int(host_xy[2 * i + 1] / row_step);                                    // :38
+        const int col = int(host_xy[2 * i] / col_step);                                        // :39
+        if (row < 0 || row > grid_rows - 1 || col < 0 || col > grid_cols - 1) {                // :41-44
+            status[i] = status_after_filter;
+            continue;
+        }
+        uint8_t &cell = free_cell[size_t(row) * grid_cols + col];
+        if (cell && status[i] == status_need_filter) cell = 0;                                 // :46-47
+        else if (!cell && status[i] == status_need_filter) status[i] = status_after_filter;    // :48-49
+    }
+    return FD_OK;
+}
+
+// ---- BRIEF -----------------------------------------------------------------------------------------
+static fd_status run_brief(fd_context *ctx, const fd_brief_params *p, const float4 *kp, const int32_t *counts, int capacity) {
+    if (p->length < 1 || p->length > 256 || p->half_patch_size < 0 || p->half_patch_size > 64 || p->reserved != 0 ||
+        (p->sampling != FD_SAMPLE_BILINEAR && p->sampling != FD_SAMPLE_TRUNCATE))
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "bad BRIEF parameters");
+    const FrameView &fv = ctx->fv;
+    FD_TRY(reserve(ctx, ctx->desc, size_t(fv.n_frames) * capacity * 32));
+    BriefArgs a = {};
+    a.fv = fv;
+    a.keypoints = kp;
+    a.kp_counts = counts;
+    a.kp_capacity = capacity;
+    a.length = p->length;
+    a.half_patch = p->half_patch_size;
+    a.sampling = p->sampling;
+    a.desc = static_cast<uint8_t *>(ctx->desc.ptr);
+    FD_CUDA(ctx, launch_brief(a, ctx->stream));
+    ++ctx->launches;
+    ctx->desc_capacity = capacity;
+    ctx->have_desc = true;
+    return FD_OK;
+}
+
+fd_status fd_describe_selected(fd_context *ctx, const fd_brief_params *params) {
+    if (!ctx || !params) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(require_frames(ctx));
+    if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
+    ctx->desc_from_user = false;
+    return run_brief(ctx, params, static_cast<const float4 *>(ctx->kp.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), ctx->kp_capacity);
+}
+
+fd_status fd_describe_points(fd_context *ctx, const fd_brief_params *params, const float *host_xy, const int32_t *host_counts, int capacity,
+                             int n_frames) {
+    if (!ctx || !params || !host_xy || !host_counts || capacity <= 0) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(require_frames(ctx));
+    if (n_frames != ctx->fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "n_frames does not match the bound frames");
+    std::vector<float4> staged(size_t(n_frames) * capacity, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int f = 0; f < n_frames; ++f) {
+        if (host_counts[f] < 0 || host_counts[f] > capacity) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "keypoint count exceeds capacity");
+        for (int i = 0; i < host_counts[f]; ++i) {
+            const size_t s = size_t(f) * capacity + i;
+            staged[s] = make_float4(host_xy[2 * s], host_xy[2 * s + 1], 0.f, 0.f);
+        }
+    }
+    FD_TRY(reserve(ctx, ctx->user_kp, staged.size() * sizeof(float4)));
+    FD_TRY(reserve(ctx, ctx->user_counts, size_t(n_frames) * 4));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->user_kp.ptr, staged.data(), staged.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->user_counts.ptr, host_counts, size_t(n_frames) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `staged` is pageable host memory going out of scope
+    ctx->user_capacity = capacity;
+    ctx->desc_from_user = true;
+    return run_brief(ctx, params, static_cast<const float4 *>(ctx->user_kp.ptr), static_cast<const int32_t *>(ctx->user_counts.ptr), capacity);
+}
+
+fd_status fd_download_descriptors(fd_context *ctx, uint8_t *host_desc, int kp_capacity) {
+    if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
+    const int nf = ctx->fv.n_frames;
+    const int w = std::min(kp_capacity, ctx->desc_capacity);
+    FD_CUDA(ctx, cudaMemcpy2DAsync(host_desc, size_t(kp_capacity) * 32, ctx->desc.ptr, size_t(ctx->desc_capacity) * 32, size_t(w) * 32, size_t(nf),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *kp_capacity) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
+    if (dev_desc) *dev_desc = static_cast<const uint8_t *>(ctx->desc.ptr);
+    if (kp_capacity) *kp_capacity = ctx->desc_capacity;
+    return FD_OK;
+}
+
+// ---- LSD field -------------------------------------------------------------------------------------
+fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_norm, float *dev_angle, int32_t *dev_sorted_idx, int32_t *dev_n_valid) {
+    if (!ctx || !params) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(require_frames(ctx));
+    const FrameView &fv = ctx->fv;
+    if (fv.rows < 2 || fv.cols < 2) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "LSD needs rows >= 2 and cols >= 2 (feature_line_detector.cpp:14)");
+    const size_t px = size_t(fv.rows) * fv.cols;
+    if (!dev_norm) {
+        FD_TRY(reserve(ctx, ctx->lsd_norm, px * fv.n_frames * 4));
+        dev_norm = static_cast<float *>(ctx->lsd_norm.ptr);
+    }
+    if (!dev_angle) {
+        FD_TRY(reserve(ctx, ctx->lsd_angle, px * fv.n_frames * 4));
+        dev_angle = static_cast<float *>(ctx->lsd_angle.ptr);
+    }
+    if ((reinterpret_cast<uintptr_t>(dev_norm) | reinterpret_cast<uintptr_t>(dev_angle)) % 16 != 0)
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "norm / angle maps must be 16-byte aligned");
+    LsdArgs a = {};
+    a.fv = fv;
+    a.min_norm = params->min_valid_gradient_norm;
+    a.norm = dev_norm;
+    a.angle = dev_angle;
+    if (params->want_sorted) {
+        FD_TRY(reserve(ctx, ctx->lsd_keys, px * fv.n_frames * 8));
+        FD_TRY(reserve(ctx, ctx->lsd_counts, size_t(fv.n_frames) * 4));
+        if (!dev_sorted_idx) {
+            FD_TRY(reserve(ctx, ctx->lsd_sorted, px * fv.n_frames * 4));
+            dev_sorted_idx = static_cast<int32_t *>(ctx->lsd_sorted.ptr);
+        }
+        FD_CUDA(ctx, cudaMemsetAsync(ctx->lsd_counts.ptr, 0, size_t(fv.n_frames) * 4, ctx->stream));
+        a.seed_keys = static_cast<uint64_t *>(ctx->lsd_keys.ptr);
+        a.seed_counts = static_cast<uint32_t *>(ctx->lsd_counts.ptr);
+    }
+    const int n_strips = (fv.cols + 127) / 128;
+    int grid;
+    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 4, 8, a.band_rows, a.n_bands, a.n_items, grid);
+    FD_CUDA(ctx, launch_lsd(a, grid, ctx->stream));
+    ++ctx->launches;
+    if (params->want_sorted) {
+        FD_CUDA(ctx, launch_seed_sort(a.seed_keys, nullptr, a.seed_counts, int64_t(px), fv.n_frames, dev_sorted_idx, fv.rows, fv.cols, ctx->stream));
+        ctx->launches += 2;
+        if (dev_n_valid)
+            FD_CUDA(ctx, cudaMemcpyAsync(dev_n_valid, ctx->lsd_counts.ptr, size_t(fv.n_frames) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->lsd_norm_p = dev_norm;
+    ctx->lsd_angle_p = dev_angle;
+    ctx->lsd_sorted_p = params->want_sorted ? dev_sorted_idx : nullptr;
+    ctx->lsd_nvalid_p = params->want_sorted ? static_cast<int32_t *>(ctx->lsd_counts.ptr) : nullptr;
+    ctx->have_lsd = true;
+    ctx->lsd_sorted_valid = params->want_sorted != 0;
+    return FD_OK;
+}
+
+fd_status fd_lsd_device_outputs(fd_context *ctx, const float **dev_norm, const float **dev_angle, const int32_t **dev_sorted_idx,
+                                const int32_t **dev_n_valid) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_lsd) return fail(ctx, FD_ERR_NOT_READY, "fd_lsd_field has not run");
+    if (dev_norm) *dev_norm = ctx->lsd_norm_p;
+    if (dev_angle) *dev_angle = ctx->lsd_angle_p;
+    if (dev_sorted_idx) *dev_sorted_idx = ctx->lsd_sorted_p;
+    if (dev_n_valid) *dev_n_valid = ctx->lsd_nvalid_p;
+    return FD_OK;
+}
+
+fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *host_angle, int32_t *host_sorted_idx, int64_t sorted_capacity,
+                          int32_t *host_n_valid) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_lsd) return fail(ctx, FD_ERR_NOT_READY, "fd_lsd_field has not run");
+    const FrameView &fv = ctx->fv;
+    if (frame < 0 || frame >= fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame out of range");
+    const size_t px = size_t(fv.rows) * fv.cols;
+    if (host_norm) FD_CUDA(ctx, cudaMemcpyAsync(host_norm, ctx->lsd_norm_p + px * frame, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_angle) FD_CUDA(ctx, cudaMemcpyAsync(host_angle, ctx->lsd_angle_p + px * frame, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t n = 0;
+    if (ctx->lsd_sorted_valid) {
+        FD_CUDA(ctx, cudaMemcpyAsync(&n, ctx->lsd_nvalid_p + frame, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (host_sorted_idx) {
+            if (int64_t(n) > sorted_capacity) return fail(ctx, FD_ERR_CAPACITY, "host sorted-index buffer too small");
+            FD_CUDA(ctx, cudaMemcpyAsync(host_sorted_idx, ctx->lsd_sorted_p + px * frame, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_n_valid) *host_n_valid = n;
+    return FD_OK;
+}
+
+fd_status fd_debug_fast_offset_bits(uint32_t count, uint32_t *out_bits, int32_t *n_segments) {
+    if (!out_bits || count == 0) return FD_ERR_INVALID_ARGUMENT;
+    const std::vector<OffsetSeg> segs = build_offset_table(count);
+    if (n_segments) *n_segments = int32_t(segs.size()) - 1;
+    size_t s = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+        while (k >= segs[s + 1].k_start) ++s;
+        out_bits[k] = segs[s].bits_start + (k - segs[s].k_start) * segs[s].step;
+    }
+    return FD_OK;
+}
+
+fd_status fd_debug_run_length_lut(uint8_t *out_65536) {
+    if (!out_65536) return FD_ERR_INVALID_ARGUMENT;
+    const std::vector<uint8_t> lut = build_run_lut();
+    std::memcpy(out_65536, lut.data(), 65536);
+    return FD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Shared device/host helpers for the sm_100a kernels behind include/fd_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdb {
+
+// ---- frame view --------------------------------------------------------------------------------
+// Device-resident batch of 8-bit frames.  `data` is 4-byte aligned and `pitch`, `frame_stride` are
+// multiples of 4, so every row can be read as aligned 32-bit words (the context re-pitches anything
+// that is not).  Words past `cols` inside the pitch may hold garbage: they only ever feed pixels
+// outside the image, whose results are discarded.
+struct FrameView {
+    const uint8_t *data;
+    int rows, cols;
+    int64_t pitch;         // bytes between rows
+    int64_t frame_stride;  // bytes between frames
+    int n_frames;
+    int words_per_row;     // readable aligned words per row = pitch / 4
+};
+
+// ---- candidate keys ------------------------------------------------------------------------------
+// One candidate = one 64-bit key: high word = bitwise complement of the order-preserving integer image
+// of the float response, low word = raster index (row * cols + col).  Sorting keys ASCENDING therefore
+// yields response DESCENDING with ties in raster order -- the tie rule this framework fixes where the
+// reference's unstable std::sort leaves it open (feature_point_detector.cpp:58).
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_cand_key(float response, uint32_t raster) {
+    return (uint64_t(~float_to_ordered(response)) << 32) | raster;
+}
+__host__ __device__ __forceinline__ float cand_key_response(uint64_t key) { return ordered_to_float(~uint32_t(key >> 32)); }
+__host__ __device__ __forceinline__ uint32_t cand_key_raster(uint64_t key) { return uint32_t(key); }
+
+#ifdef __CUDACC__
+// ---- small PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t ld_word(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Warp-aggregated append of up to `n_mine` keys per lane into a per-frame slot.  Returns false if the
+// slot overflowed (the counter still advances, so the host sees the true demand).
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t *counter, uint32_t n_mine) {
+    // inclusive scan of n_mine across the warp
+    uint32_t incl = n_mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane_id() >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (total != 0) {
+        if (lane_id() == 31) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    return base + incl - n_mine;
+}
+#endif  // __CUDACC__
+
+}  // namespace fdb

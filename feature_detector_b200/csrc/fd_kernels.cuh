@@ -1,0 +1,113 @@
+// Internal launch interface between the C-ABI layer (fd_api.cu) and the kernels.
+#pragma once
+
+#include "fd_common.cuh"
+
+namespace fdb {
+
+// ---- kernel 2: FAST --------------------------------------------------------------------------
+constexpr int FAST_THREADS = 256;
+
+// One linear piece of the reference's running float offset (fast.cpp:85,93): for masked-in pixel
+// index k in [k_start, next.k_start) the offset's BIT PATTERN is bits_start + (k - k_start) * step.
+struct OffsetSeg {
+    uint32_t k_start, bits_start, step;
+};
+
+struct FastArgs {
+    FrameView fv;
+    int diff;                 // kMinPixelDiffValue
+    float thr;                // kMinValidResponse
+    const uint8_t *lut;       // 65536-entry longest-circular-run table (device)
+    const OffsetSeg *segs;    // n_seg pieces + one sentinel (k_start = 0xFFFFFFFF)
+    int n_seg;
+    uint64_t *cand_keys;      // n_frames slots of cand_capacity keys
+    uint32_t *cand_counts;    // n_frames
+    uint32_t cand_capacity;
+    uint8_t *score_map;       // optional dense score map (n_frames * rows * cols), may be null
+    int score_aligned;        // score_map rows can be written as aligned words
+    int n_strips, n_bands, band_rows;
+    int64_t n_items;
+};
+size_t fast_smem_bytes(int n_seg);
+cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream);
+
+// ---- kernel 1: Harris / Shi-Tomasi -------------------------------------------------------------
+constexpr int CORNER_THREADS = 256;
+constexpr int CORNER_STRIP_OUT = 126;  // NMS-complete columns per 128-column warp strip
+
+struct CornerArgs {
+    FrameView fv;
+    int kind;                 // 0 Harris, 1 Shi-Tomasi (reference formula: larger eigenvalue)
+    float thr;                // kMinValidResponse
+    float alpha;              // Harris kAlpha
+    float inv_cnt, inv_cnt2;  // 1/9 and its square, rounded as the reference rounds them (harris.cpp:71-72)
+    uint64_t *cand_keys;
+    uint32_t *cand_counts;
+    uint32_t cand_capacity;
+    float *response_map;      // optional dense thresholded response map, may be null
+    int n_strips, n_bands, band_rows;
+    int64_t n_items;
+};
+cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream);
+
+// ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
+constexpr int SELECT_THREADS = 512;
+
+struct SelectArgs {
+    int rows, cols, n_frames;
+    uint64_t *cand_keys;            // in: unsorted; out: sorted ascending (= response descending, raster ties)
+    uint64_t *cand_scratch;         // same size, for the out-of-shared-memory sort path
+    const uint32_t *cand_counts;
+    uint32_t cand_capacity;
+    int min_distance;
+    uint32_t needed;
+    const int32_t *existing_counts; // per frame, may be null (= 0)
+    float4 *keypoints;              // n_frames slots of kp_capacity (x, y, response, 0)
+    int32_t *kp_counts;
+    int kp_capacity;
+    uint32_t *cell_scratch;         // global fallback for the accepted-point cell grid (per frame), may be null
+    int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
+    int cells_in_smem;
+    int smem_sort_capacity;         // keys that fit the shared-memory sort
+    uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
+};
+size_t select_smem_bytes(const SelectArgs &a);
+cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
+
+// ---- kernel 4: steered BRIEF --------------------------------------------------------------------
+struct BriefArgs {
+    FrameView fv;
+    const float4 *keypoints;   // slots of kp_capacity per frame: (x, y, *, *)
+    const int32_t *kp_counts;
+    int kp_capacity;
+    int length, half_patch, sampling;
+    uint8_t *desc;             // 32 bytes per keypoint slot
+};
+cudaError_t launch_brief(const BriefArgs &args, cudaStream_t stream);
+
+// ---- kernel 5: LSD gradient / level-line field --------------------------------------------------
+constexpr int LSD_THREADS = 256;
+struct LsdArgs {
+    FrameView fv;
+    float min_norm;
+    float *norm;               // n_frames * (rows-1) * (cols-1)
+    float *angle;
+    uint64_t *seed_keys;       // optional: per-frame slots of (rows-1)*(cols-1) keys
+    uint32_t *seed_counts;
+    int n_bands, band_rows;
+    int64_t n_items;
+};
+cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
+// Sort each frame's seed keys ascending and strip them to int32 map indices.
+cudaError_t launch_seed_sort(uint64_t *keys, uint64_t *scratch, const uint32_t *counts, int64_t slot, int n_frames, int32_t *sorted_idx,
+                             int map_rows, int map_cols, cudaStream_t stream);
+
+// ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
+cudaError_t launch_segment_sort(uint64_t *keys, uint64_t *scratch, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity,
+                                cudaStream_t stream);
+
+// ---- mask from pre-existing features ------------------------------------------------------------
+// (feature_point_detector.cpp:76-98) -- filled in by fd_mask.cu
+
+}  // namespace fdb

@@ -1,0 +1,183 @@
+/* fd_b200.h -- C ABI of the B200-native dense feature-detection path.
+ *
+ * The reference (Horizon1026/Feature_Detector) has no plugin / FFI layer: its boundary is the public
+ * C++ class API, all entry points non-virtual.  "Drop-in" therefore means link-time
+ * substitution: the C++ classes under feature_detector_b200/cpp/ keep the reference's names,
+ * namespaces, Options structs and accessors, and their bodies call THIS C ABI.  Each group of entry
+ * points below cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every call returns an fd_status (0 = OK); fd_last_error(ctx) gives the text of the last failure;
+ *   - there is NO CPU fallback anywhere behind this header: without a CUDA device fd_create fails;
+ *   - one context = one device + one stream; calls are asynchronous on that stream unless they copy to
+ *     pageable host memory or are documented as synchronising; a context is not re-entrant;
+ *   - "frames" are 8-bit grayscale images.  Host frames are pitch-less and contiguous like the
+ *     reference's GrayImage (feature_point_harris_detector.cpp:31 `data + r * cols`); device frames may
+ *     carry a row pitch and a frame stride;
+ *   - per-frame outputs live in fixed-capacity slots so that a batch needs no host round trip:
+ *     slot f of an array with capacity C starts at element f*C, and counts[f] says how many are valid.
+ */
+#ifndef FD_B200_H_
+#define FD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fd_context fd_context;
+
+typedef enum fd_status {
+    FD_OK = 0,
+    FD_ERR_INVALID_ARGUMENT = 1,
+    FD_ERR_NO_DEVICE = 2,       /* no usable CUDA device: there is no CPU path to fall back to */
+    FD_ERR_CUDA = 3,            /* a CUDA runtime call or kernel failed; see fd_last_error */
+    FD_ERR_OUT_OF_MEMORY = 4,
+    FD_ERR_CAPACITY = 5,        /* a per-frame slot overflowed (candidates); raise the capacity and retry */
+    FD_ERR_NOT_READY = 6        /* a stage was asked for before the stage that feeds it */
+} fd_status;
+
+/* Detector kinds.  SHI_TOMAS reproduces the reference, which returns the LARGER eigenvalue
+ * (feature_point_shi_tomas_detector.cpp:94-100). */
+typedef enum fd_detector_kind { FD_HARRIS = 0, FD_SHI_TOMAS = 1, FD_FAST = 2 } fd_detector_kind;
+
+/* FeaturePointDetector::Options (feature_point_detector.h:15-20) plus the three detectors' private
+ * SubOptions (harris_detector.h:12-15, shi_tomas_detector.h:12-14, fast_detector.h:12-15), which the
+ * reference gives no accessor for; defaults below are the reference's values. */
+typedef struct fd_detect_params {
+    int32_t kind;                 /* fd_detector_kind */
+    float min_valid_response;     /* kMinValidResponse, default 0.1f */
+    int32_t min_feature_distance; /* kMinFeatureDistance, default 15 */
+    uint32_t needed_feature_num;  /* DetectGoodFeatures argument */
+    float harris_alpha;           /* SubOptions::kAlpha, default 0.04f (Harris only) */
+    int32_t fast_n;               /* SubOptions::kN, default 12: only toggles the pre-check (>= 12) */
+    int32_t fast_min_pixel_diff;  /* SubOptions::kMinPixelDiffValue, default 15 */
+    int32_t reserved;             /* must be 0 */
+} fd_detect_params;
+
+/* BriefDescriptor::Options (descriptor_brief.h:16-19). */
+typedef struct fd_brief_params {
+    int32_t length;               /* kLength, 1..256, default 256 */
+    int32_t half_patch_size;      /* kHalfPatchSize, default 8 (orientation patch) */
+    int32_t sampling;             /* fd_brief_sampling */
+    int32_t reserved;             /* must be 0 */
+} fd_brief_params;
+
+/* Float-coordinate pixel fetch of the absent upstream Image class (guess G1). */
+typedef enum fd_brief_sampling {
+    FD_SAMPLE_BILINEAR = 0,       /* four-tap bilinear around the truncated coordinate (the parity mode) */
+    FD_SAMPLE_TRUNCATE = 1        /* nearest-below pixel; no reference parity available */
+} fd_brief_sampling;
+
+/* FeatureLineDetector::Options (feature_line_detector.h:40-45): only the field the map stage reads. */
+typedef struct fd_lsd_params {
+    float min_valid_gradient_norm; /* kMinValidGradientNorm, default 20.0f */
+    int32_t want_sorted;           /* 1: also produce the seed order (norm descending) */
+} fd_lsd_params;
+
+/* One selected keypoint: the reference returns Vec2(x = col, y = row) as floats
+ * (feature_point_detector.cpp:67); response is the candidate's score. */
+typedef struct fd_keypoint {
+    float x, y;
+    float response;
+    int32_t reserved;
+} fd_keypoint;
+
+/* One candidate as the reference's std::pair<float, Pixel> (feature_point_detector.h:36,51). */
+typedef struct fd_candidate {
+    float response;
+    int32_t x, y;
+} fd_candidate;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+fd_status fd_create(int device_ordinal, fd_context **out_ctx);
+fd_status fd_destroy(fd_context *ctx);
+const char *fd_last_error(const fd_context *ctx);
+const char *fd_version(void);
+/* Use an externally owned cudaStream_t (e.g. PyTorch's current stream); NULL restores the context's own. */
+fd_status fd_set_stream(fd_context *ctx, void *cuda_stream);
+fd_status fd_sync(fd_context *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t fd_launch_count(const fd_context *ctx);
+
+/* ---- frames (replaces the GrayImage argument of every reference entry point) ------------------- */
+/* Copy n_frames contiguous host frames into context-owned device memory (pitched for aligned loads). */
+fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames);
+/* Use frames that already live on the device.  pitch / frame_stride in bytes. */
+fd_status fd_bind_device_frames(fd_context *ctx, const uint8_t *dev_frames, int rows, int cols, int64_t pitch, int64_t frame_stride,
+                                int n_frames);
+
+/* ---- pre-existing features (the in/out `features` argument, feature_point_detector.cpp:12-16,90-98)
+ * counts[f] features for frame f at xy[(f*capacity + i)*2 + {0,1}] (host memory, floats as in Vec2).
+ * They mask their (2d+1)^2 neighbourhood out of candidate generation and count toward needed_feature_num.
+ * Pass n_frames = 0 to clear. */
+fd_status fd_set_existing_features(fd_context *ctx, const float *host_xy, const int32_t *host_counts, int capacity, int n_frames);
+
+/* ---- kernels 1-3: FeaturePointDetector::DetectGoodFeatures (feature_point_detector.cpp:7-25) ---- */
+/* Candidate generation (ComputeCandidates: harris.cpp:5-15, shi_tomas.cpp:5-15, fast.cpp:83-98) followed
+ * by sort + greedy min-distance selection (SelectGoodFeatures, feature_point_detector.cpp:54-74) for every
+ * bound frame.  cand_capacity bounds candidates per frame (0 = rows*cols, always sufficient);
+ * FD_ERR_CAPACITY is reported by fd_sync / the download calls if a frame overflowed. */
+fd_status fd_detect(fd_context *ctx, const fd_detect_params *params, int cand_capacity);
+/* Candidate generation only (no selection); candidates stay unsorted in the context. */
+fd_status fd_compute_candidates(fd_context *ctx, const fd_detect_params *params, int cand_capacity);
+/* Optional dense outputs written during the NEXT fd_detect / fd_compute_candidates (device pointers,
+ * n_frames*rows*cols elements, row-major, no pitch); NULL disables.  response: Harris / Shi-Tomasi
+ * responses_ (thresholded, harris.cpp:74-103); score: raw FAST score 0..16 (fast.cpp:11-81). */
+fd_status fd_set_dense_outputs(fd_context *ctx, float *dev_response_map, uint8_t *dev_fast_score_map);
+
+/* Results.  Keypoints: only the NEW features, in selection order (append them after the pre-existing
+ * ones to get the reference's vector).  Candidates: sorted by response descending, ties in raster order.
+ * Host variants synchronise; the device variant returns context-owned pointers valid until the next
+ * detect call (kp slots have capacity *kp_capacity). */
+fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *host_counts, int kp_capacity);
+fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out);
+fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts);
+fd_status fd_device_keypoints(fd_context *ctx, const fd_keypoint **dev_kp, const int32_t **dev_counts, int *kp_capacity);
+
+/* FeaturePointDetector::SparsifyFeatures (feature_point_detector.cpp:27-52): first-come grid filter over an
+ * existing feature list.  Pure host-side integer logic over at most a few thousand points; kept in the
+ * library so the drop-in class has one implementation.  status is in/out (n entries). */
+fd_status fd_sparsify(const float *host_xy, int n, int image_rows, int image_cols, int grid_rows, int grid_cols,
+                      uint8_t status_need_filter, uint8_t status_after_filter, uint8_t *status);
+
+/* ---- kernel 4: Descriptor<BriefType>::Compute (descriptor.h:28-40, descriptor_brief.cpp:8-50) --- */
+/* Describe the keypoints selected by the last fd_detect (device-resident, no host round trip). */
+fd_status fd_describe_selected(fd_context *ctx, const fd_brief_params *params);
+/* Describe caller-supplied keypoints: counts[f] points for frame f at xy[(f*capacity+i)*2] (host memory). */
+fd_status fd_describe_points(fd_context *ctx, const fd_brief_params *params, const float *host_xy, const int32_t *host_counts,
+                             int capacity, int n_frames);
+/* Descriptors: 32 bytes per keypoint, bit i at byte i/8, bit position i%8 (LSB first); bits >= length are 0.
+ * Slot layout follows the keypoints that were described. */
+fd_status fd_download_descriptors(fd_context *ctx, uint8_t *host_desc, int kp_capacity);
+fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *kp_capacity);
+
+/* ---- kernel 5: FeatureLineDetector::ComputeLineLevelAngleMap (feature_line_detector.cpp:56-97) -- */
+/* For every bound frame: gradient norm and level-line angle maps, written as rows x cols floats, row-major
+ * (the reference's pixels_ is (rows-1) x (cols-1); the extra last row / column is zero, which keeps every
+ * map row 16-byte aligned for vector stores).  angle is 0 where the pixel is not valid.  If want_sorted:
+ * the valid pixels ordered by norm descending, ties in the reference's column-major push order, as
+ * (row * cols + col) indices.  Outputs are device pointers, 16-byte aligned: norm / angle
+ * n_frames*rows*cols floats; sorted_idx n_frames*rows*cols int32 (one slot per frame); n_valid n_frames
+ * int32.  Any may be context-owned: pass NULL and fetch with fd_lsd_device_outputs. */
+fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_norm, float *dev_angle, int32_t *dev_sorted_idx,
+                       int32_t *dev_n_valid);
+fd_status fd_lsd_device_outputs(fd_context *ctx, const float **dev_norm, const float **dev_angle, const int32_t **dev_sorted_idx,
+                                const int32_t **dev_n_valid);
+fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *host_angle, int32_t *host_sorted_idx, int64_t sorted_capacity,
+                          int32_t *host_n_valid);
+
+/* ---- diagnostics of the host-built tables (no GPU needed; used by the CPU test-suite) ------------- */
+/* Bit patterns of the FAST running offset (fast.cpp:85,93) for masked-in pixel index k = 0..count-1, as
+ * evaluated from the piecewise-linear table the kernel uses; *n_segments = pieces in that table. */
+fd_status fd_debug_fast_offset_bits(uint32_t count, uint32_t *out_bits, int32_t *n_segments);
+/* The 65536-entry longest-circular-run table the FAST kernel looks scores up in. */
+fd_status fd_debug_run_length_lut(uint8_t *out_65536);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FD_B200_H_ */

@@ -1,0 +1,101 @@
+"""CPU suite, part 2: the C-ABI library loads, exports every symbol include/fd_b200.h declares, fails
+loudly without a GPU, and its host-built tables are right."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import feature_detector_b200 as fd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "fd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = fd.load_library()
+    names = _declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fd_b200.h but not exported"
+
+
+def test_python_binding_covers_the_header():
+    lib = fd.load_library()
+    for n in _declared_functions():
+        assert getattr(lib, n).argtypes is not None, f"binding for {n} missing"
+
+
+def test_no_cpu_fallback_without_device():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fd.FdError) as e:
+        fd.Context(0)
+    assert e.value.status == 2  # FD_ERR_NO_DEVICE
+
+
+def test_product_does_not_touch_the_oracle():
+    """No file of the product package may import, link or open anything under oracle/."""
+    pkg = os.path.join(ROOT, "feature_detector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("oracle/ port", ""), f"{f} mentions the oracle"
+                assert "libfd_ref" not in text and "libfd_oracle" not in text
+
+
+def test_fast_offset_table_matches_the_float_loop():
+    lib = fd.load_library()
+    n = 300_000
+    out = np.zeros(n, np.uint32)
+    nseg = C.c_int32(0)
+    assert lib.fd_debug_fast_offset_bits(n, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(nseg)) == 0
+    off = np.float32(1e-5)
+    inc = np.float32(1e-5)
+    exp = np.empty(n, np.float32)
+    for k in range(n):  # feature_point_fast_detector.cpp:85,93
+        exp[k] = off
+        off = np.float32(off + inc)
+    assert np.array_equal(exp.view(np.uint32), out)
+    assert 8 <= nseg.value <= 64
+    # the offset crosses 0.1 near the 10 000th masked-in pixel (rounding drift moves it a little)
+    first = int(np.argmax(out.view(np.float32) > 0.1))
+    assert 9990 <= first <= 10010
+
+
+def test_fast_run_length_lut():
+    lib = fd.load_library()
+    lut = np.zeros(65536, np.uint8)
+    assert lib.fd_debug_run_length_lut(lut.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+    rng = np.random.default_rng(0)
+    for m in [0, 0xFFFF, 0x8001, 0x00FF, 0xF00F, 0x7FFF, 0xAAAA] + rng.integers(0, 65536, 300).tolist():
+        bits = [(m >> i) & 1 for i in range(16)]
+        best = run = 0
+        for i in range(32):  # walk the ring twice (fast.cpp:55-78)
+            run = run + 1 if bits[i % 16] else 0
+            best = max(best, run)
+        assert lut[m] == min(best, 16)
+
+
+def test_sparsify_host_logic(port, vectors):
+    st = fd.sparsify(vectors["sparsify.features"], 480, 752, 1, 2, vectors["sparsify.status_in"])
+    assert np.array_equal(st, vectors["sparsify.status_out"])
+    rng = np.random.default_rng(5)
+    for rows, cols, gr, gc in [(480, 752, 12, 12), (720, 1280, 8, 10), (100, 100, 3, 4)]:
+        f = np.stack([rng.uniform(-30, cols + 30, 300), rng.uniform(-30, rows + 30, 300)], 1).astype(np.float32)
+        s0 = rng.integers(0, 3, 300).astype(np.uint8)
+        assert np.array_equal(fd.sparsify(f, rows, cols, 1, 2, s0, gr, gc), port.sparsify(f, rows, cols, 1, 2, s0, gr, gc))
+    # size mismatch -> all ones first (feature_point_detector.cpp:29-31)
+    assert np.array_equal(fd.sparsify(f, 480, 752, 1, 2, None), port.sparsify(f, 480, 752, 1, 2, np.zeros(0, np.uint8)))

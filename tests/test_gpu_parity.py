@@ -1,0 +1,274 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the CPU checker on the same inputs.
+
+Bit-exact for FAST scores / responses, candidate sets, keypoint lists (raster tie rule), BRIEF bits, LSD
+norms; Harris / Shi-Tomasi responses are compared bitwise too (BASELINE.json allows 1e-4 relative, SURVEY.md
+H1 shows bitwise is reachable); LSD angles within 1e-5 (different atan2f implementations).
+"""
+import numpy as np
+import pytest
+
+import feature_detector_b200 as fd
+from conftest import fnv
+from oracle.bindings import FAST, HARRIS, SHI_TOMAS
+from oracle.tiecheck import greedy_replay, same_up_to_ties
+
+pytestmark = pytest.mark.gpu
+
+KIND = {"fast": FAST, "fast9": FAST, "harris": HARRIS, "shi": SHI_TOMAS}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = fd.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _gpu_detect(ctx, im, kind, thr, d, n, fast_n=12, cap=0):
+    ctx.upload(im)
+    ctx.detect(fd.DetectParams(kind, thr, d, n, fast_n=fast_n), cap)
+    kp, cnt = ctx.keypoints(max(n, 1))
+    cand = ctx.candidates(0)
+    feats = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32)
+    return feats, cand, kp[0, :cnt[0]]
+
+
+def _assert_same_candidates(cand, o):
+    """GPU candidates (sorted: response desc, raster ties) vs checker candidates (its own sorted order)."""
+    assert len(cand) == o["n_cand"]
+    g = np.lexsort((cand["x"], cand["y"]))
+    c = np.lexsort((o["cand_xy"][:, 0], o["cand_xy"][:, 1]))
+    assert np.array_equal(cand["x"][g], o["cand_xy"][c, 0]) and np.array_equal(cand["y"][g], o["cand_xy"][c, 1])
+    assert np.array_equal(cand["response"][g].view(np.uint32), o["cand_resp"][c].view(np.uint32))
+    # and the GPU's own order is (response desc, y, x)
+    order = np.lexsort((cand["x"], cand["y"], -cand["response"].astype(np.float64)))
+    assert np.array_equal(order, np.arange(len(cand)))
+
+
+def _assert_same_features(feats, cand, o, shape, d, n):
+    if np.array_equal(feats, o["features"]):
+        return
+    # identical except for ties: same sorted multiset, and each list is the greedy replay of its own order
+    assert same_up_to_ties(o["cand_resp"], o["cand_xy"], cand["response"], np.stack([cand["x"], cand["y"]], 1))
+    replay, _ = greedy_replay(np.stack([cand["x"], cand["y"]], 1), shape[0], shape[1], d, n)
+    assert np.array_equal(replay, feats)
+
+
+def test_golden_detector_cases(ctx, frames, kat):
+    """Config 0 of BASELINE.json (image.png, the demo option values) and the synthetic goldens, no oracle needed."""
+    n = 0
+    for c in kat["cases"]:
+        if c["detector"] not in KIND:
+            continue
+        im = frames[c["frame"]]
+        feats, cand, _ = _gpu_detect(ctx, im, KIND[c["detector"]], c["thr"], c["dist"], c["needed"], c["fast_n"])
+        assert len(cand) == c["n_cand"], c
+        g = np.lexsort((cand["x"], cand["y"]))
+        flat = np.zeros((len(cand), 3), np.uint32)
+        flat[:, 0] = cand["response"][g].view(np.uint32)
+        flat[:, 1] = cand["x"][g]
+        flat[:, 2] = cand["y"][g]
+        assert fnv(flat) == c["cand_hash"], c
+        assert len(feats) == c["n_feat_raster_ties"]
+        assert fnv(feats.astype("<i4")) == c["feat_hash_raster_ties"], c
+        n += 1
+    assert n >= 21
+
+
+@pytest.mark.parametrize("shape_idx", [(752, 480, 21), (333, 217, 5), (1280, 720, 2), (130, 70, 9), (64, 48, 1), (1001, 37, 3)])
+@pytest.mark.parametrize("case", [("fast", 10.0, 20, 200, 12), ("fast", 10.0, 20, 200, 9), ("fast", 0.1, 15, 300, 12), ("fast", 3.0, 7, 100, 9),
+                                  ("harris", 30.0, 20, 200, 12), ("harris", 0.1, 15, 1000, 12), ("shi", 40.0, 20, 1000, 12),
+                                  ("shi", 0.1, 4, 3000, 12)])
+def test_detect_vs_checker(ctx, checker, shape_idx, case):
+    from feature_detector_b200.synth import synth
+    w, h, idx = shape_idx
+    name, thr, d, n, fast_n = case
+    im = synth(w, h, idx)
+    o = checker.detect(KIND[name], im, thr, d, n, fast_n=fast_n)
+    feats, cand, _ = _gpu_detect(ctx, im, KIND[name], thr, d, n, fast_n)
+    _assert_same_candidates(cand, o)
+    _assert_same_features(feats, cand, o, im.shape, d, n)
+
+
+def test_dense_maps_vs_checker(ctx, checker, torch_cuda, frames):
+    torch = torch_cuda
+    for name, im in frames.items():
+        h, w = im.shape
+        resp = torch.full((h, w), -7.0, dtype=torch.float32, device="cuda")
+        score = torch.full((h, w), 99, dtype=torch.uint8, device="cuda")
+        ctx.upload(im)
+        ctx.set_dense_outputs(resp.data_ptr(), score.data_ptr())
+        try:
+            for kind, thr in ((HARRIS, 0.1), (HARRIS, 30.0), (SHI_TOMAS, 0.1), (SHI_TOMAS, 40.0)):
+                ctx.compute_candidates(fd.DetectParams(kind, thr, 15, 10))
+                ctx.sync()
+                o = checker.detect(kind, im, thr, 15, 10, want_response=True, want_candidates=False)
+                got = resp.cpu().numpy()
+                assert np.array_equal(got.view(np.uint32), o["response"].view(np.uint32)), (name, kind, thr)
+            for fast_n in (12, 9):
+                ctx.compute_candidates(fd.DetectParams(FAST, 10.0, 15, 10, fast_n=fast_n))
+                ctx.sync()
+                assert np.array_equal(score.cpu().numpy(), checker.fast_score_map(im, fast_n, 15)), (name, fast_n)
+        finally:
+            ctx.set_dense_outputs(0, 0)
+
+
+def test_fast_pixel_diff_parameter(ctx, checker, torch_cuda):
+    from feature_detector_b200.synth import synth
+    torch = torch_cuda
+    im = synth(320, 200, 8)
+    score = torch.zeros(im.shape, dtype=torch.uint8, device="cuda")
+    ctx.upload(im)
+    ctx.set_dense_outputs(0, score.data_ptr())
+    try:
+        for diff in (0, 1, 15, 40, 255):
+            ctx.compute_candidates(fd.DetectParams(FAST, 10.0, 15, 10, fast_n=9, fast_min_pixel_diff=diff))
+            ctx.sync()
+            assert np.array_equal(score.cpu().numpy(), checker.fast_score_map(im, 9, diff)), diff
+    finally:
+        ctx.set_dense_outputs(0, 0)
+
+
+def test_batch_equals_single_frames(ctx, checker):
+    """A batch is processed frame by frame identically (frames are independent)."""
+    from feature_detector_b200.synth import synth_batch
+    batch = synth_batch(752, 480, 6, start=100)
+    for kind, thr, d, n, fast_n in ((FAST, 10.0, 20, 200, 9), (HARRIS, 30.0, 20, 200, 12)):
+        ctx.upload(batch)
+        ctx.detect(fd.DetectParams(kind, thr, d, n, fast_n=fast_n))
+        kp, cnt = ctx.keypoints(n)
+        counts = ctx.candidate_counts()
+        for f in range(len(batch)):
+            o = checker.detect(kind, batch[f], thr, d, n, fast_n=fast_n)
+            assert counts[f] == o["n_cand"]
+            feats = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1)
+            cand = ctx.candidates(f)
+            _assert_same_candidates(cand, o)
+            _assert_same_features(feats, cand, o, batch[f].shape, d, n)
+
+
+def test_candidate_capacity_overflow_is_reported(ctx):
+    from feature_detector_b200.synth import synth
+    ctx.upload(synth(752, 480, 0))
+    ctx.detect(fd.DetectParams(HARRIS, 30.0, 20, 200), 1000)  # ~23k candidates on this frame
+    with pytest.raises(fd.FdError) as e:
+        ctx.keypoints(200)
+    assert e.value.status == 5
+
+
+def test_needed_zero_and_flat_images(ctx, checker):
+    from feature_detector_b200.synth import synth
+    im = synth(160, 120, 3)
+    feats, _, _ = _gpu_detect(ctx, im, HARRIS, 30.0, 20, 0)
+    assert len(feats) == 1 and np.array_equal(feats, checker.detect(HARRIS, im, 30.0, 20, 0)["features"])
+    flat = np.full((64, 64), 77, np.uint8)
+    for kind, thr in ((HARRIS, 0.1), (SHI_TOMAS, 0.1), (FAST, 10.0)):
+        feats, cand, _ = _gpu_detect(ctx, flat, kind, thr, 15, 100)
+        assert len(feats) == 0 and len(cand) == 0
+    feats, cand, _ = _gpu_detect(ctx, flat, FAST, 0.001, 15, 100)
+    o = checker.detect(FAST, flat, 0.001, 15, 100)
+    _assert_same_candidates(cand, o)
+    assert np.array_equal(feats, o["features"])
+    for shape in [(4, 4), (6, 9), (7, 7), (5, 5)]:
+        tiny = np.arange(shape[0] * shape[1], dtype=np.uint8).reshape(shape) * 9
+        for kind in (HARRIS, SHI_TOMAS, FAST):
+            feats, cand, _ = _gpu_detect(ctx, tiny, kind, 1.0, 2, 10)
+            o = checker.detect(kind, tiny, 1.0, 2, 10)
+            _assert_same_candidates(cand, o)
+
+
+def test_brief_golden_and_checker(ctx, checker, frames, kat, vectors):
+    for c in kat["cases"]:
+        if c["detector"] != "brief":
+            continue
+        im = frames[c["frame"]]
+        kp = vectors[f"{c['frame']}.brief.{c['set']}.kp"]
+        ctx.upload(im)
+        cap = ctx.describe_points(fd.BriefParams(c["length"], 8), [kp])
+        desc = ctx.descriptors(cap)[0, :len(kp)]
+        assert np.array_equal(desc[:, :(c["length"] + 7) // 8], vectors[f"{c['frame']}.brief.{c['set']}.desc"]), c
+        assert not desc[:, (c["length"] + 7) // 8:].any()
+        assert fnv(np.ascontiguousarray(desc[:, :(c["length"] + 7) // 8])) == c["hash"]
+    # other patch sizes / lengths and keypoints right at the border limit, against the checker
+    from feature_detector_b200.synth import synth
+    im = synth(400, 300, 12)
+    rng = np.random.default_rng(2)
+    kp = np.stack([rng.uniform(0, 400, 200), rng.uniform(0, 280, 200)], 1).astype(np.float32)
+    kp[:40] = np.floor(kp[:40])
+    kp[40] = (19.0, 19.0)
+    kp[41] = (18.999, 50.0)
+    kp[42] = (400 - 19.0, 100.0)
+    for length, hp in ((256, 8), (200, 12), (31, 3), (256, 0)):
+        ctx.upload(im)
+        cap = ctx.describe_points(fd.BriefParams(length, hp), [kp])
+        bits = fd.unpack_bits(ctx.descriptors(cap)[0, :len(kp)], length)
+        ok, exp = checker.brief(im, kp, length, hp)
+        assert ok and np.array_equal(bits, exp), (length, hp)
+
+
+def test_detect_then_describe_stays_on_device(ctx, checker, image_png):
+    """FAST -> select -> BRIEF without a host round trip (config 1 pipeline), against the checker run stage by stage."""
+    ctx.upload(image_png)
+    ctx.detect(fd.DetectParams(FAST, 10.0, 20, 200, fast_n=12))
+    ctx.describe_selected(fd.BriefParams(256, 8))
+    kp, cnt = ctx.keypoints(200)
+    desc = ctx.descriptors(200)
+    o = checker.detect(FAST, image_png, 10.0, 20, 200)
+    feats = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1)
+    assert np.array_equal(feats, o["features"]) and cnt[0] == 84
+    ok, exp = checker.brief(image_png, o["features"], 256, 8)
+    assert np.array_equal(fd.unpack_bits(desc[0, :cnt[0]]), exp)
+
+
+def test_lsd_field_vs_checker(ctx, checker, frames):
+    from feature_detector_b200.synth import synth
+    cases = dict(frames)
+    cases["s1920"] = synth(1920, 1080, 1)
+    cases["tiny"] = synth(9, 7, 1)
+    for name, im in cases.items():
+        h, w = im.shape
+        ctx.upload(im)
+        ctx.lsd_field(fd.LsdParams(20.0, 1))
+        g = ctx.lsd_download(0)
+        o = checker.lsd_map(im)
+        norm, angle = g["norm"][:h - 1, :w - 1], g["angle"][:h - 1, :w - 1]
+        assert not g["norm"][h - 1:].any() and not g["norm"][:, w - 1:].any()
+        assert np.array_equal(norm.view(np.uint32), o["norm"].view(np.uint32)), name           # bit-exact
+        valid = norm > 20.0
+        assert np.array_equal(valid, o["valid"].astype(bool))
+        assert not angle[~valid].any()
+        assert np.max(np.abs(angle[valid] - o["angle"][valid]), initial=0.0) <= 1e-5, name       # north_star tolerance
+        assert g["n_valid"] == int(o["valid"].sum())
+        # seed order: norm descending; ties in column-major push order (= a stable sort of the reference's push order)
+        rows_, cols_ = g["sorted_idx"] // w, g["sorted_idx"] % w
+        seq = norm[rows_, cols_]
+        assert np.all(np.diff(seq) <= 0)
+        exp_rc = o["sorted_rc"]
+        assert np.array_equal(seq, o["norm"][exp_rc[:, 0], exp_rc[:, 1]])
+        cm = cols_.astype(np.int64) * h + rows_
+        same = np.diff(seq) == 0
+        assert np.all(np.diff(cm)[same] > 0)
+        assert len(np.unique(g["sorted_idx"])) == len(g["sorted_idx"])
+
+
+def test_bound_device_frames_with_pitch(ctx, checker, torch_cuda):
+    """Frames that already live on the device, including an unaligned pitch (re-pitched internally)."""
+    from feature_detector_b200.synth import synth_batch
+    torch = torch_cuda
+    batch = synth_batch(333, 217, 3, start=40)
+    for pitch in (333, 336, 400):
+        buf = torch.zeros((3, 217, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, :, :333] = torch.from_numpy(batch).cuda()
+        ctx.bind_device(buf.data_ptr(), 217, 333, 3, pitch=pitch)
+        ctx.detect(fd.DetectParams(FAST, 10.0, 20, 200, fast_n=9))
+        kp, cnt = ctx.keypoints(200)
+        for f in range(3):
+            o = checker.detect(FAST, batch[f], 10.0, 20, 200, fast_n=9)
+            assert np.array_equal(np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1), o["features"])

@@ -1,0 +1,151 @@
+"""CPU suite, part 1: the oracle is pinned to the reference.
+
+* the committed golden vectors (generated from oracle/_ref, i.e. the reference's own code) must be
+  reproduced by the plain-C port -- this runs everywhere, including the GPU box where /root/reference
+  does not exist;
+* where oracle/_ref is present, port and reference are also compared directly on more frames.
+"""
+import numpy as np
+import pytest
+
+from conftest import fnv
+from oracle.bindings import FAST, HARRIS, SHI_TOMAS
+from oracle.tiecheck import greedy_replay, same_up_to_ties
+
+KINDS = {"fast": FAST, "fast9": FAST, "harris": HARRIS, "shi": SHI_TOMAS}
+
+
+def _cand_record(o):
+    xy, r = o["cand_xy"], o["cand_resp"]
+    order = np.lexsort((xy[:, 0], xy[:, 1]))
+    flat = np.zeros((len(r), 3), np.uint32)
+    flat[:, 0] = r[order].view(np.uint32)
+    flat[:, 1] = xy[order, 0]
+    flat[:, 2] = xy[order, 1]
+    return flat
+
+
+def test_golden_image_is_the_reference_example(image_png, kat):
+    import hashlib
+    assert hashlib.sha256(image_png.tobytes()).hexdigest() == kat["image_sha256"]
+    # SURVEY.md section 8c quotes this digest for examples/image.png
+    assert kat["image_sha256"] == "7aed1139f1833cd6f600bad397066109d0a578a7535f7178dd5cab45f90d2190"
+
+
+def test_survey_known_answers_are_in_the_golden_file(kat):
+    """The survey's table (section 8c) was produced independently; the regenerated goldens must agree."""
+    want = {("fast", 10.0): (962, "14b52e7f58f59c8f", 84, "dd67c5129a1e7e40"),
+            ("fast", 0.1): (343669, "e479cac1f25d041f", 200, "80b9d39bf6d4ded1"),
+            ("harris", 30.0): (12894, "dc38c516de0fade7", 200, "32c324070cbd3b8b"),
+            ("harris", 0.1): (14542, "801265c5432c71c5", 200, "97927df081f7973b"),
+            ("shi", 40.0): (3742, "e2785ec440d6c9a5", 200, "73062c834d19eb5b"),
+            ("shi", 0.1): (13123, "474475b49489e281", 591, "7fba4523e43d10c4")}
+    seen = 0
+    for c in kat["cases"]:
+        key = (c.get("detector"), c.get("thr"))
+        if c.get("frame") == "image" and key in want:
+            n_cand, ch, n_feat, fh = want[key]
+            assert (c["n_cand"], c["cand_hash"], c["n_feat"], c["feat_hash"]) == (n_cand, ch, n_feat, fh)
+            seen += 1
+    assert seen == len(want)
+
+
+def test_port_reproduces_golden_detector_cases(port, frames, kat, vectors):
+    n = 0
+    for c in kat["cases"]:
+        if c["detector"] not in KINDS:
+            continue
+        im = frames[c["frame"]]
+        o = port.detect(KINDS[c["detector"]], im, c["thr"], c["dist"], c["needed"], fast_n=c["fast_n"], want_response=c["detector"] in ("harris", "shi"))
+        assert o["n_cand"] == c["n_cand"]
+        assert fnv(_cand_record(o)) == c["cand_hash"]
+        if "resp_hash" in c:
+            assert fnv(o["response"]) == c["resp_hash"]
+            assert int(np.count_nonzero(o["response"])) == c["resp_nonzero"]
+        # features: raster tie rule (port) -- equals the reference's list unless the case is tie sensitive
+        assert fnv(o["features"].astype("<i4")) == c["feat_hash_raster_ties"]
+        if not c["tie_sensitive"]:
+            assert fnv(o["features"].astype("<i4")) == c["feat_hash"]
+        key = f"{c['frame']}.{c['detector']}.{c['thr']:g}.{c['dist']}.{c['needed']}.features"
+        assert np.array_equal(vectors[key].astype(np.float32), o["features"])
+        n += 1
+    assert n >= 21
+
+
+def test_port_reproduces_golden_scores_brief_lsd(port, frames, kat, vectors):
+    for c in kat["cases"]:
+        im = frames[c["frame"]]
+        if c["detector"] == "fast_score":
+            s = port.fast_score_map(im, c["fast_n"], 15)
+            assert fnv(s) == c["score_hash"]
+            assert np.bincount(s[3:-3, 3:-3].ravel(), minlength=17).tolist() == c["hist"]
+        elif c["detector"] == "brief":
+            kp = vectors[f"{c['frame']}.brief.{c['set']}.kp"]
+            ok, bits = port.brief(im, kp, c["length"], 8)
+            assert ok and int(bits.sum()) == c["ones"] and int((bits.sum(1) == 0).sum()) == c["all_zero"]
+            packed = np.packbits(bits, axis=1, bitorder="little")
+            assert fnv(packed) == c["hash"]
+            assert np.array_equal(packed, vectors[f"{c['frame']}.brief.{c['set']}.desc"])
+        elif c["detector"] == "lsd":
+            m = port.lsd_map(im)
+            assert int(m["valid"].sum()) == c["n_valid"]
+            assert fnv(m["norm"]) == c["norm_hash"]
+            assert fnv(m["angle"]) == c["angle_hash"]  # same glibc atan2f as the generator
+            s = m["sorted_rc"]
+            assert fnv(m["norm"][s[:, 0], s[:, 1]]) == c["sorted_norm_hash"]
+
+
+def test_port_preseeded_and_sparsify_golden(port, image_png, kat, vectors):
+    c = [c for c in kat["cases"] if c["detector"] == "harris_preseeded81"][0]
+    pre = np.array([[15 * i, 15 * j] for i in range(1, 10) for j in range(1, 10)], np.float32)  # test_feature_point_detector.cpp:52-56
+    o = port.detect(HARRIS, image_png, c["thr"], c["dist"], c["needed"], pre=pre)
+    assert o["n_cand"] == c["n_cand"] and len(o["features"]) == c["n_feat"]
+    assert fnv(o["features"].astype("<i4")) == c["feat_hash"] == "85bd4f625b5448b3"
+    st = port.sparsify(vectors["sparsify.features"], 480, 752, 1, 2, vectors["sparsify.status_in"])
+    assert np.array_equal(st, vectors["sparsify.status_out"])
+
+
+def test_port_equals_reference_on_more_frames(port, ref):
+    from feature_detector_b200.synth import synth
+    for (w, h, idx) in [(752, 480, 11), (640, 360, 2), (97, 61, 4), (1280, 720, 1)]:
+        im = synth(w, h, idx)
+        for kind, thr, d, n, fn in [(FAST, 10, 20, 200, 0), (FAST, 10, 20, 200, 9), (FAST, 0.1, 15, 50, 0), (HARRIS, 30, 20, 200, 0),
+                                    (SHI_TOMAS, 40, 20, 1000, 0), (HARRIS, 0.1, 3, 5000, 0)]:
+            a = ref.detect(kind, im, thr, d, n, fast_n=fn, want_response=True, want_mask=True)
+            b = port.detect(kind, im, thr, d, n, fast_n=fn, want_response=True, want_mask=True)
+            assert np.array_equal(_cand_record(a), _cand_record(b))
+            assert np.array_equal(a["response"].view(np.uint32), b["response"].view(np.uint32))
+            if np.array_equal(a["features"], b["features"]):
+                assert np.array_equal(a["mask"], b["mask"])
+            else:  # identical except for ties
+                assert same_up_to_ties(a["cand_resp"], a["cand_xy"], b["cand_resp"], b["cand_xy"])
+                for res in (a, b):
+                    replay, _ = greedy_replay(res["cand_xy"], h, w, d, n)
+                    assert np.array_equal(replay, res["features"])
+        for fn in (12, 9):
+            assert np.array_equal(ref.fast_score_map(im, fn, 15), port.fast_score_map(im, fn, 15))
+        kp = ref.detect(HARRIS, im, 20, 20, 100, want_candidates=False)["features"]
+        if len(kp):
+            assert np.array_equal(ref.brief(im, kp)[1], port.brief(im, kp)[1])
+        a, b = ref.lsd_map(im), port.lsd_map(im)
+        for k in ("norm", "angle"):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32))
+        assert np.array_equal(a["valid"], b["valid"])
+        sa, sb = a["sorted_rc"], b["sorted_rc"]
+        assert np.array_equal(a["norm"][sa[:, 0], sa[:, 1]], b["norm"][sb[:, 0], sb[:, 1]])
+
+
+def test_edge_cases_port(port):
+    # needed = 0 still yields one feature (feature_point_detector.cpp:67-68); tiny / flat images yield none
+    from feature_detector_b200.synth import synth
+    im = synth(160, 120, 3)
+    assert len(port.detect(HARRIS, im, 30, 20, 0)["features"]) == 1
+    flat = np.full((64, 64), 77, np.uint8)
+    assert port.detect(HARRIS, flat, 0.1, 15, 100)["n_cand"] == 0
+    assert port.detect(FAST, flat, 10, 15, 100)["n_cand"] == 0
+    o = port.detect(FAST, flat, 0.001, 15, 100)  # the running offset alone crosses the threshold
+    assert o["n_cand"] == 58 * 58 - 99
+    for shape in [(4, 4), (6, 9), (7, 7)]:
+        tiny = np.zeros(shape, np.uint8)
+        for kind in (HARRIS, SHI_TOMAS, FAST):
+            assert port.detect(kind, tiny, 10, 5, 10)["n_cand"] == 0
