@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 W, H = 752, 480
 THR, DIST, NEEDED = 10.0, 20, 200
 BRIEF_LEN, BRIEF_HALF = 256, 8
-CAND_CAPACITY = 8192  # per-frame candidate slots (the demo threshold yields a few hundred to a few thousand)
+CAND_CAPACITY = 65536  # per-frame candidate slots (kN=9 at the demo threshold yields up to a few 10^4 on busy frames)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -221,7 +221,8 @@ def main():
     n, px = args.frames, H * W
 
     ctx = fd.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # the kernels AND the timing events go on this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     det = fd.DetectParams(fd.FAST, THR, DIST, NEEDED, fast_n=args.fast_n)
     brief = fd.BriefParams(BRIEF_LEN, BRIEF_HALF)

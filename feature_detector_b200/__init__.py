@@ -84,6 +84,7 @@ def load_library():
         "fd_last_error": (C.c_char_p, [vp]),
         "fd_version": (C.c_char_p, []),
         "fd_set_stream": (C.c_int, [vp, vp]),
+        "fd_own_stream": (vp, [vp]),
         "fd_sync": (C.c_int, [vp]),
         "fd_launch_count": (C.c_uint64, [vp]),
         "fd_upload_frames": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int]),
@@ -164,6 +165,9 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream_handle):
+        """Run on the given cudaStream_t handle (0 = the legacy default stream); None = back to the context's own stream."""
+        if cuda_stream_handle is None:
+            cuda_stream_handle = self._lib.fd_own_stream(self._h)
         self._ck(self._lib.fd_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
 
     def sync(self):

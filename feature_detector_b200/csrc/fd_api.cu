@@ -375,9 +375,11 @@ const char *fd_last_error(const fd_context *ctx) { return ctx ? ctx->err.c_str()
 fd_status fd_set_stream(fd_context *ctx, void *cuda_stream) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     return FD_OK;
 }
+
+void *fd_own_stream(const fd_context *ctx) { return ctx ? static_cast<void *>(ctx->own_stream) : nullptr; }
 
 fd_status fd_sync(fd_context *ctx) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
@@ -395,8 +397,12 @@ fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows
     const int64_t pitch = (int64_t(cols) + 15) / 16 * 16;
     const int64_t stride = pitch * rows;
     FD_TRY(reserve(ctx, ctx->owned_frames, size_t(stride) * n_frames));
-    FD_CUDA(ctx, cudaMemcpy2DAsync(ctx->owned_frames.ptr, size_t(pitch), host_frames, size_t(cols), size_t(cols), size_t(rows) * n_frames,
-                                   cudaMemcpyHostToDevice, ctx->stream));
+    if (pitch == cols) {
+        FD_CUDA(ctx, cudaMemcpyAsync(ctx->owned_frames.ptr, host_frames, size_t(stride) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        FD_CUDA(ctx, cudaMemcpy2DAsync(ctx->owned_frames.ptr, size_t(pitch), host_frames, size_t(cols), size_t(cols), size_t(rows) * n_frames,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, pitch, stride, n_frames, int(pitch / 4)};
     ctx->frames_bound = true;
     ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;

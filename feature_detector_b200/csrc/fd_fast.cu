@@ -78,10 +78,15 @@ __device__ __forceinline__ void ring_step(const Row &r, uint32_t kbE, uint32_t k
     }
 }
 
-// Offset table lookup: bit pattern of the reference's running float `offset` for masked-in pixel index k.
-__device__ __forceinline__ uint32_t offset_bits(const OffsetSeg *__restrict__ segs, int &seg, uint32_t k) {
-    while (k >= segs[seg + 1].k_start) ++seg;
-    return segs[seg].bits_start + (k - segs[seg].k_start) * segs[seg].step;
+// Offset table lookup: bit pattern of the reference's running float `offset` for masked-in pixel index k
+// (binary search over the <= 64 linear pieces; only candidate-bearing rows get here).
+__device__ __forceinline__ uint32_t offset_bits(const OffsetSeg *__restrict__ segs, int n_seg, uint32_t k) {
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].k_start <= k) lo = mid; else hi = mid - 1;
+    }
+    return segs[lo].bits_start + (k - segs[lo].k_start) * segs[lo].step;
 }
 
 template <bool PRECHECK>
@@ -163,100 +168,116 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
         const int row_end = min(row_begin + p.band_rows, fv.rows - 3);
         if (row_begin >= row_end) continue;
 
+        // Rows are read as three aligned words per lane.  Addresses are clamped instead of predicated: a
+        // clamped word only ever feeds pixels outside the interior, whose results are masked below.
         const int w = strip * 32 + lane;                                // this lane's word in the row
+        const int wl = min(max(w - 1, 0), fv.words_per_row - 1) * 4;
+        const int wc = min(w, fv.words_per_row - 1) * 4;
+        const int wr = min(w + 1, fv.words_per_row - 1) * 4;
         const uint8_t *fbase = fv.data + int64_t(frame) * fv.frame_stride;
-        const bool ok0 = (w - 1 >= 0) && (w - 1 < fv.words_per_row);
-        const bool ok1 = (w < fv.words_per_row);
-        const bool ok2 = (w + 1 < fv.words_per_row);
-        auto load_row = [&](int row, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-            w0 = w1 = w2 = 0u;
-            if (row < fv.rows) {
-                const uint8_t *rp = fbase + int64_t(row) * fv.pitch + 4 * int64_t(w);
-                if (ok0) w0 = ld_word(rp - 4);
-                if (ok1) w1 = ld_word(rp);
-                if (ok2) w2 = ld_word(rp + 4);
-            }
-        };
+        const int last_row = fv.rows - 1;
+#define FD_LOAD_ROW(ROW, W0, W1, W2)                                          \
+        {                                                                     \
+            const uint8_t *rp__ = fbase + int64_t(min(ROW, last_row)) * fv.pitch; \
+            W0 = ld_word(rp__ + wl);                                          \
+            W1 = ld_word(rp__ + wc);                                          \
+            W2 = ld_word(rp__ + wr);                                          \
+        }
 
         Row rw[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             uint32_t w0, w1, w2;
-            load_row(row_begin - 3 + i, w0, w1, w2);
+            FD_LOAD_ROW(row_begin - 3 + i, w0, w1, w2);
             make_row(rw[i], w0, w1, w2);
         }
 
         const int col0 = 4 * w;
-        // which of this lane's 4 pixels are interior columns [3, cols-4]
-        uint32_t col_ok = 0u;
+        uint32_t col_ok = 0u;  // 0xFF per interior column [3, cols-4] of this lane
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (col0 + j >= 3 && col0 + j <= fv.cols - 4) col_ok |= 0xFFu << (8 * j);
-        int seg = 0;
-        uint32_t *counter = p.cand_counts + frame;
-        uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
-        uint8_t *score_row_base = p.score_map ? p.score_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
 
-        int row = row_begin;
-        while (row < row_end) {
+        // Smallest score that can become a candidate anywhere in this band: the offset only grows with k, so
+        // fl(score + offset) <= fl(score + offset at the band's last pixel).  Rows whose scores all stay below it
+        // skip the float path entirely (with the demo threshold 10 that is almost every row).
+        uint32_t need_add;  // adding it to the packed scores sets bit 7 of every byte whose score >= s_need
+        {
+            const uint32_t k_hi = uint32_t(row_end - 1 - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
+            const float off_hi = __uint_as_float(offset_bits(segs, p.n_seg, k_hi));
+            int s_need = 17;
+            for (int sc = 16; sc >= 0; --sc)
+                if (__fadd_rn(float(sc), off_hi) > p.thr) s_need = sc;
+            need_add = (s_need == 0) ? 0x80808080u : (s_need > 16 ? 0u : (0x80u - uint32_t(s_need)) * 0x01010101u);
+        }
+        uint8_t *score_base = p.score_map ? p.score_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
+
+        for (int row = row_begin; row < row_end; row += 7) {
+            uint32_t spv[7];
+            uint32_t hits = 0u;  // warp-uniform: phases with at least one possible candidate
 #pragma unroll
             for (int ph = 0; ph < 7; ++ph) {
-                if (row < row_end) {  // warp-uniform
-                    uint32_t n0, n1, n2;
-                    load_row(row + 4, n0, n1, n2);  // prefetch the row that enters the window next step
-                    uint32_t sp;
-                    fast_step<PRECHECK>(rw[(ph + 0) % 7], rw[(ph + 1) % 7], rw[(ph + 2) % 7], rw[(ph + 3) % 7], rw[(ph + 4) % 7],
-                                        rw[(ph + 5) % 7], rw[(ph + 6) % 7], kbias, lut, sp);
-                    sp &= col_ok;
-                    if (score_row_base != nullptr && col0 < fv.cols) {
-                        uint8_t *dst = score_row_base + int64_t(row) * fv.cols + col0;
-                        if (p.score_aligned && col0 + 3 < fv.cols) {
-                            *reinterpret_cast<uint32_t *>(dst) = sp;
-                        } else {
+                const int r = row + ph;
+                uint32_t n0, n1, n2;
+                FD_LOAD_ROW(r + 4, n0, n1, n2);  // the row that enters the window next step
+                uint32_t sp;
+                fast_step<PRECHECK>(rw[(ph + 0) % 7], rw[(ph + 1) % 7], rw[(ph + 2) % 7], rw[(ph + 3) % 7], rw[(ph + 4) % 7],
+                                    rw[(ph + 5) % 7], rw[(ph + 6) % 7], kbias, lut, sp);
+                sp &= col_ok;
+                const bool live = r < row_end;  // rows past the band are computed on clamped data and dropped
+                if (score_base != nullptr && live && col0 < fv.cols) {
+                    uint8_t *dst = score_base + int64_t(r) * fv.cols + col0;
+                    if (p.score_aligned && col0 + 3 < fv.cols) {
+                        *reinterpret_cast<uint32_t *>(dst) = sp;
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col0 + j < fv.cols) dst[j] = uint8_t(sp >> (8 * j));
+                        for (int j = 0; j < 4; ++j)
+                            if (col0 + j < fv.cols) dst[j] = uint8_t(sp >> (8 * j));
+                    }
+                }
+                spv[ph] = sp;
+                const bool hit = live && ((((sp + need_add) | (need_add & 0x80808080u)) & col_ok & 0x80808080u) != 0u);
+                if (__any_sync(0xffffffffu, hit)) hits |= 1u << ph;
+                make_row(rw[(ph + 0) % 7], n0, n1, n2);
+            }
+            // response = score + offset(k), k = index of the pixel among the masked-in interior pixels in raster
+            // order (fast.cpp:85-93); candidates are appended with one atomic per warp and row.
+            while (hits != 0u) {
+                const int ph = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                uint32_t sp = spv[0];
+#pragma unroll
+                for (int q = 1; q < 7; ++q) sp = (ph == q) ? spv[q] : sp;
+                const int r = row + ph;
+                uint32_t mine = 0u;
+                float resp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    resp[j] = 0.0f;
+                    if ((col_ok >> (8 * j)) & 1u) {
+                        const uint32_t k = uint32_t(r - 3) * uint32_t(inner_cols) + uint32_t(col0 + j - 3);
+                        const float off = __uint_as_float(offset_bits(segs, p.n_seg, k));
+                        const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);
+                        if (v > p.thr) {
+                            resp[j] = v;
+                            mine |= 1u << j;
                         }
                     }
-                    // response = score + offset(k), k = index of the pixel among the masked-in interior pixels
-                    // in raster order (fast.cpp:85-93).  Skip the float work when nothing in the warp can pass.
-                    const uint32_t k_first = uint32_t(row - 3) * uint32_t(inner_cols) + uint32_t(max(col0 - 3, 0));
-                    const uint32_t k_row_last = uint32_t(row - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
-                    const float off_hi = __uint_as_float(offset_bits(segs, seg, min(k_first + 3u, k_row_last)));
-                    if (__any_sync(0xffffffffu, (sp != 0u) || (off_hi > p.thr))) {
-                        uint32_t n_mine = 0u;
-                        float resp[4];
+                }
+                if (__any_sync(0xffffffffu, mine != 0u)) {
+                    uint32_t pos = warp_reserve(p.cand_counts + frame, __popc(mine));
+                    uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            resp[j] = 0.0f;
-                            if ((col_ok >> (8 * j)) & 1u) {
-                                int s = seg > 0 ? seg - 1 : 0;  // k is non-decreasing per lane except inside one step
-                                const uint32_t k = uint32_t(row - 3) * uint32_t(inner_cols) + uint32_t(col0 + j - 3);
-                                const float off = __uint_as_float(offset_bits(segs, s, k));
-                                const float r = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);
-                                if (r > p.thr) {
-                                    resp[j] = r;
-                                    n_mine += 1u << (8 * j);
-                                }
-                            }
-                        }
-                        const uint32_t cnt = __popc(n_mine);
-                        if (__any_sync(0xffffffffu, cnt != 0u)) {
-                            uint32_t pos = warp_reserve(counter, cnt);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if ((n_mine >> (8 * j)) & 1u) {
-                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[j], uint32_t(row) * uint32_t(fv.cols) + uint32_t(col0 + j));
-                                    ++pos;
-                                }
-                            }
+                    for (int j = 0; j < 4; ++j) {
+                        if ((mine >> j) & 1u) {
+                            if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[j], uint32_t(r) * uint32_t(fv.cols) + uint32_t(col0 + j));
+                            ++pos;
                         }
                     }
-                    make_row(rw[(ph + 0) % 7], n0, n1, n2);
-                    ++row;
                 }
             }
         }
+#undef FD_LOAD_ROW
     }
 }
 

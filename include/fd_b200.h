@@ -96,8 +96,10 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx);
 fd_status fd_destroy(fd_context *ctx);
 const char *fd_last_error(const fd_context *ctx);
 const char *fd_version(void);
-/* Use an externally owned cudaStream_t (e.g. PyTorch's current stream); NULL restores the context's own. */
+/* Run on an externally owned cudaStream_t (e.g. PyTorch's current stream).  The handle is used as given, so
+ * NULL is the legacy default stream; pass fd_own_stream(ctx) to return to the context's own stream. */
 fd_status fd_set_stream(fd_context *ctx, void *cuda_stream);
+void *fd_own_stream(const fd_context *ctx);
 fd_status fd_sync(fd_context *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t fd_launch_count(const fd_context *ctx);
