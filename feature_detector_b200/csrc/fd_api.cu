@@ -177,6 +177,7 @@ fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
         FD_TRY(reserve(ctx, ctx->segs, segs.size() * sizeof(OffsetSeg)));
         FD_CUDA(ctx, cudaMemcpyAsync(ctx->segs.ptr, segs.data(), segs.size() * sizeof(OffsetSeg), cudaMemcpyHostToDevice, ctx->stream));
         FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (segs.size() > size_t(FAST_MAX_SEGS)) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "FAST offset table has too many pieces for this frame size");
         ctx->n_seg = int(segs.size()) - 1;
         ctx->seg_count_covered = want;
     }
@@ -185,7 +186,7 @@ fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
 
 // Split the interior rows into bands so that every resident warp gets several work items.
 void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_frames, int warps_per_cta, int ctas_per_sm, int min_band,
-                int &band_rows, int &n_bands, int64_t &n_items, int &grid) {
+                int band_multiple, int &band_rows, int &n_bands, int64_t &n_items, int &grid) {
     grid = ctx->sm_count * ctas_per_sm;
     const int64_t total_warps = int64_t(grid) * warps_per_cta;
     const int64_t base_items = int64_t(n_frames) * n_strips;
@@ -193,6 +194,7 @@ void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_fr
     want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, std::max(1, interior_rows / min_band)));
     band_rows = int((interior_rows + want_bands - 1) / want_bands);
     band_rows = std::max(band_rows, 1);
+    band_rows = (band_rows + band_multiple - 1) / band_multiple * band_multiple;  // kernels that unroll their row loop
     n_bands = (interior_rows + band_rows - 1) / band_rows;
     n_items = base_items * n_bands;
     const int64_t ctas_needed = (n_items + warps_per_cta - 1) / warps_per_cta;
@@ -219,7 +221,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not implemented in this build");
     const FrameView &fv = ctx->fv;
     const int64_t px = int64_t(fv.rows) * fv.cols;
-    if (px >= (int64_t(1) << 31)) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame too large");
+    if (fv.rows > 65535 || fv.cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
     const uint32_t cap = cand_capacity > 0 ? uint32_t(std::min<int64_t>(cand_capacity, px)) : uint32_t(px);
     ctx->cand_capacity = cap;
     FD_TRY(reserve(ctx, ctx->keys, size_t(fv.n_frames) * cap * 8));
@@ -250,7 +252,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
             int grid;
-            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, 2, 16, a.band_rows, a.n_bands, a.n_items, grid);
+            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, 2, 14, 7, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
             ++ctx->launches;
         }
@@ -273,7 +275,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.response_map = ctx->resp_map;
             a.n_strips = (fv.cols - 4 + CORNER_STRIP_OUT - 1) / CORNER_STRIP_OUT;
             int grid;
-            plan_bands(ctx, fv.rows - 4, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, a.band_rows, a.n_bands, a.n_items, grid);
+            plan_bands(ctx, fv.rows - 4, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
             ++ctx->launches;
         }
@@ -293,7 +295,6 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     a.cols = fv.cols;
     a.n_frames = fv.n_frames;
     a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
-    a.cand_scratch = nullptr;
     a.cand_counts = static_cast<const uint32_t *>(ctx->counts.ptr);
     a.cand_capacity = ctx->cand_capacity;
     a.min_distance = p->min_feature_distance;
@@ -306,17 +307,15 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     a.cells_x = (fv.cols + cell - 1) / cell;
     a.cells_y = (fv.rows + cell - 1) / cell;
     const size_t cell_bytes = size_t(a.cells_x) * a.cells_y * 4;
-    a.cells_in_smem = cell_bytes <= 64 * 1024;
+    a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
+    a.cells_in_smem = cell_bytes <= 16 * 1024;
     if (!a.cells_in_smem) {
         FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
-    int sort_cap = 1024;
-    while (uint32_t(sort_cap) < ctx->cand_capacity && sort_cap < 16384) sort_cap <<= 1;
-    a.smem_sort_capacity = sort_cap;
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     FD_CUDA(ctx, launch_select(a, ctx->stream));
-    ++ctx->launches;
+    ctx->launches += 2;
     ctx->candidates_sorted = true;
     ctx->have_keypoints = true;
     return FD_OK;
@@ -486,10 +485,10 @@ fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!ctx->candidates_sorted) std::sort(keys.begin(), keys.end());  // presentation order only; selection never takes this path
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t raster = cand_key_raster(keys[i]);
+        const uint32_t xy = cand_key_xy(keys[i]);
         host_cand[i].response = cand_key_response(keys[i]);
-        host_cand[i].x = int32_t(raster % uint32_t(ctx->fv.cols));
-        host_cand[i].y = int32_t(raster / uint32_t(ctx->fv.cols));
+        host_cand[i].x = int32_t(xy & 0xFFFFu);
+        host_cand[i].y = int32_t(xy >> 16);
     }
     return FD_OK;
 }
@@ -657,11 +656,11 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
     }
     const int n_strips = (fv.cols + 127) / 128;
     int grid;
-    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 4, 8, a.band_rows, a.n_bands, a.n_items, grid);
+    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 4, 8, 1, a.band_rows, a.n_bands, a.n_items, grid);
     FD_CUDA(ctx, launch_lsd(a, grid, ctx->stream));
     ++ctx->launches;
     if (params->want_sorted) {
-        FD_CUDA(ctx, launch_seed_sort(a.seed_keys, nullptr, a.seed_counts, int64_t(px), fv.n_frames, dev_sorted_idx, fv.rows, fv.cols, ctx->stream));
+        FD_CUDA(ctx, launch_seed_sort(a.seed_keys, a.seed_counts, int64_t(px), fv.n_frames, dev_sorted_idx, fv.cols, ctx->stream));
         ctx->launches += 2;
         if (dev_n_valid)
             FD_CUDA(ctx, cudaMemcpyAsync(dev_n_valid, ctx->lsd_counts.ptr, size_t(fv.n_frames) * 4, cudaMemcpyDeviceToDevice, ctx->stream));

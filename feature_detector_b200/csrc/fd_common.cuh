@@ -22,9 +22,9 @@ struct FrameView {
 
 // ---- candidate keys ------------------------------------------------------------------------------
 // One candidate = one 64-bit key: high word = bitwise complement of the order-preserving integer image
-// of the float response, low word = raster index (row * cols + col).  Sorting keys ASCENDING therefore
-// yields response DESCENDING with ties in raster order -- the tie rule this framework fixes where the
-// reference's unstable std::sort leaves it open (feature_point_detector.cpp:58).
+// of the float response, low word = (row << 16) | col.  Sorting keys ASCENDING therefore yields response
+// DESCENDING with ties in raster order -- the tie rule this framework fixes where the reference's unstable
+// std::sort leaves it open (feature_point_detector.cpp:58).  Frames are limited to 65535 x 65535.
 __host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
 #ifdef __CUDA_ARCH__
     uint32_t b = __float_as_uint(f);
@@ -41,11 +41,11 @@ __host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
     union { float f; uint32_t u; } c; c.u = b; return c.f;
 #endif
 }
-__host__ __device__ __forceinline__ uint64_t make_cand_key(float response, uint32_t raster) {
-    return (uint64_t(~float_to_ordered(response)) << 32) | raster;
+__host__ __device__ __forceinline__ uint64_t make_cand_key(float response, uint32_t row, uint32_t col) {
+    return (uint64_t(~float_to_ordered(response)) << 32) | (row << 16) | col;
 }
 __host__ __device__ __forceinline__ float cand_key_response(uint64_t key) { return ordered_to_float(~uint32_t(key >> 32)); }
-__host__ __device__ __forceinline__ uint32_t cand_key_raster(uint64_t key) { return uint32_t(key); }
+__host__ __device__ __forceinline__ uint32_t cand_key_xy(uint64_t key) { return uint32_t(key); }  // (row << 16) | col
 
 #ifdef __CUDACC__
 // ---- small PTX wrappers ---------------------------------------------------------------------------

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 if ((mine >> j) & 1u) {
-                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[p2][j], uint32_t(m) * uint32_t(fv.cols) + uint32_t(c0 + j));
+                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[p2][j], uint32_t(m), uint32_t(c0 + j));
                                     ++pos;
                                 }
                             }

@@ -5,76 +5,87 @@
 // Design (sm_100a, no tensor cores: nothing here is a contraction)
 //   * a warp owns a 128-pixel-wide column strip of one frame and streams down a band of rows; each lane
 //     owns 4 adjacent pixels (one aligned 32-bit word per row) and keeps the 7 rows the Bresenham ring
-//     spans in registers, pre-split into 16-bit lanes (even / odd pixels) so that one 32-bit add compares
-//     two pixels against the centre +/- threshold: bit 15 of (ring + 0x8000 - diff - 1 - centre) is the
-//     "brighter" flag, bit 15 of (0x8000 - diff - 1 + centre - ring) the "darker" flag.  No saturation
-//     is needed: the 16-bit lanes give the int32 semantics of fast.cpp:12-14 exactly;
-//   * one PRMT with sign replication turns the two flag words (even, odd) into four byte masks, one
-//     LOP3 files them under ring bit i: after 16 ring positions each pixel has a 16-bit brighter mask and
-//     a 16-bit darker mask;
+//     spans in registers as packed bytes;
+//   * the segment test runs on the FMA pipe in packed half precision (pixel values 0..255 and their
+//     differences are exact in fp16): one PRMT turns two neighbouring bytes into a half2 (0x6400 | byte is
+//     the fp16 number 1024 + byte, and the common 1024 cancels in every difference), one saturating HADD2
+//     yields the brighter (or darker) flag of two pixels as exactly 0.0 / 1.0 -- the int32 comparisons of
+//     fast.cpp:12-14,44-52 on integers -- and one HFMA2 files it under ring bit i of an accumulator that
+//     starts at 1024.0, so the low byte of the accumulator's bit pattern IS the 8-bit ring mask.  The
+//     integer pipe (half the FMA pipe's issue rate on this part) only does the byte shuffles;
 //   * the score (longest circular run of set bits, 0..16; fast.cpp:55-78) is a 64 KiB shared-memory
-//     table lookup per mask, skipped for lanes whose masks are all zero;
+//     table lookup per 16-bit mask, skipped for lanes whose masks are all zero;
 //   * the kN >= 12 pre-check (fast.cpp:20-42) is evaluated in its closed form -- right, bottom and left
 //     ring pixels all brighter, or all darker -- on ring positions 4, 8, 12 first, and a
 //     warp whose 128 pixels all fail skips the other 13 positions;
 //   * response = float(score) + offset(k) with the reference's sequentially accumulated float offset
-//     reproduced exactly from a piecewise-linear table of its bit pattern;
-//   * candidates (response > threshold) are appended to the frame's slot with one atomic per warp.
+//     reproduced exactly from a piecewise-linear table of its bit pattern; rows that
+//     cannot reach the threshold (score below the band's minimum useful score) never enter the float path;
+//   * candidates (response > threshold) are appended to the frame's slot with one atomic per warp and row.
 // HBM traffic: every input byte is read once from DRAM (neighbouring lanes / row bands re-read it from
 // L1 / L2); output is the candidate list (+1 B/px when the dense score map is requested).
+#include <cuda_fp16.h>
+
 #include "fd_kernels.cuh"
 
 namespace fdb {
 
 namespace {
 
+// One image row as this lane sees it: packed bytes of columns x-4..x-1 (w0), x..x+3 (w1), x+4..x+7 (w2) and
+// the two words that straddle them, xl = columns x-1..x+2 and xr = columns x+3..x+6.
 struct Row {
-    uint32_t E1, O1, O0, E2, SE01, SO01, SE12, SO12;
+    uint32_t w0, w1, w2, xl, xr;
 };
 
 __device__ __forceinline__ void make_row(Row &r, uint32_t w0, uint32_t w1, uint32_t w2) {
-    // even pixels -> 16-bit lanes (px0, px2); odd pixels -> (px1, px3)
-    const uint32_t e0 = prmt(w0, 0u, 0x4240u);
-    r.O0 = prmt(w0, 0u, 0x4341u);
-    r.E1 = prmt(w1, 0u, 0x4240u);
-    r.O1 = prmt(w1, 0u, 0x4341u);
-    r.E2 = prmt(w2, 0u, 0x4240u);
-    const uint32_t o2 = prmt(w2, 0u, 0x4341u);
-    r.SE01 = __funnelshift_r(e0, r.E1, 16);    // pixels (x-2, x)
-    r.SO01 = __funnelshift_r(r.O0, r.O1, 16);  // pixels (x-1, x+1)
-    r.SE12 = __funnelshift_r(r.E1, r.E2, 16);  // pixels (x+2, x+4)
-    r.SO12 = __funnelshift_r(r.O1, o2, 16);    // pixels (x+3, x+5)
+    r.w0 = w0;
+    r.w1 = w1;
+    r.w2 = w2;
+    r.xl = __funnelshift_r(w0, w1, 24);
+    r.xr = __funnelshift_r(w1, w2, 24);
 }
 
-// (even-lane word, odd-lane word) of the four pixels at column offset DX in row `r`.
-template <int DX>
-__device__ __forceinline__ void ring_words(const Row &r, uint32_t &e, uint32_t &o) {
-    if (DX == 0) { e = r.E1; o = r.O1; }
-    else if (DX == 1) { e = r.O1; o = r.SE12; }
-    else if (DX == -1) { e = r.SO01; o = r.E1; }
-    else if (DX == 2) { e = r.SE12; o = r.SO12; }
-    else if (DX == -2) { e = r.SE01; o = r.SO01; }
-    else if (DX == 3) { e = r.SO12; o = r.E2; }
-    else { e = r.O0; o = r.SE01; }  // DX == -3
+__device__ __forceinline__ __half2 h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+
+// Pixels (x+S, x+S+1) of row `r` as half2 (1024 + value each).
+template <int S>
+__device__ __forceinline__ __half2 pair(const Row &r) {
+    constexpr uint32_t M = 0x64646464u;
+    if (S == -3) return h2(prmt(r.w0, M, 0x4241u));
+    if (S == -2) return h2(prmt(r.w0, M, 0x4342u));
+    if (S == -1) return h2(prmt(r.xl, M, 0x4140u));
+    if (S == 0) return h2(prmt(r.w1, M, 0x4140u));
+    if (S == 1) return h2(prmt(r.w1, M, 0x4241u));
+    if (S == 2) return h2(prmt(r.w1, M, 0x4342u));
+    if (S == 3) return h2(prmt(r.xr, M, 0x4140u));
+    if (S == 4) return h2(prmt(r.w2, M, 0x4140u));
+    return h2(prmt(r.w2, M, 0x4241u));  // S == 5
 }
 
+// Ring masks as fp16 accumulators: value 1024 + (8-bit mask); index 0 = pixels (0,1), 1 = pixels (2,3).
 struct Acc {
-    uint32_t bLo, bHi, dLo, dHi;  // per pixel byte: ring bits 0-7 / 8-15 of the brighter / darker mask
+    __half2 bLo[2], bHi[2], dLo[2], dHi[2];
 };
 
 template <int I, int DX>
-__device__ __forceinline__ void ring_step(const Row &r, uint32_t kbE, uint32_t kbO, uint32_t kdE, uint32_t kdO, Acc &a) {
-    uint32_t e, o;
-    ring_words<DX>(r, e, o);
-    const uint32_t mb = prmt(e + kbE, o + kbO, 0xFBD9u);  // 0xFF per pixel whose ring pixel I is brighter
-    const uint32_t md = prmt(kdE - e, kdO - o, 0xFBD9u);  // ... darker
-    constexpr uint32_t bit = 0x01010101u << (I & 7);
+__device__ __forceinline__ void ring_step(const Row &r, const __half2 (&nhi)[2], const __half2 (&lo)[2], Acc &a) {
+    constexpr uint32_t wbits = (0x3C00u + (uint32_t(I & 7) << 10)) * 0x00010001u;  // half2(2^(I&7), 2^(I&7))
+    const __half2 w = h2(wbits);
+    const __half2 r01 = pair<DX>(r), r23 = pair<DX + 2>(r);
+    const __half2 fb0 = __hadd2_sat(r01, nhi[0]), fb1 = __hadd2_sat(r23, nhi[1]);      // ring > centre + diff
+    const __half2 fd0 = __hadd2_sat(lo[0], __hneg2(r01)), fd1 = __hadd2_sat(lo[1], __hneg2(r23));  // ring < centre - diff
     if (I < 8) {
-        a.bLo |= mb & bit;
-        a.dLo |= md & bit;
+        a.bLo[0] = __hfma2(fb0, w, a.bLo[0]);
+        a.bLo[1] = __hfma2(fb1, w, a.bLo[1]);
+        a.dLo[0] = __hfma2(fd0, w, a.dLo[0]);
+        a.dLo[1] = __hfma2(fd1, w, a.dLo[1]);
     } else {
-        a.bHi |= mb & bit;
-        a.dHi |= md & bit;
+        a.bHi[0] = __hfma2(fb0, w, a.bHi[0]);
+        a.bHi[1] = __hfma2(fb1, w, a.bHi[1]);
+        a.dHi[0] = __hfma2(fd0, w, a.dHi[0]);
+        a.dHi[1] = __hfma2(fd1, w, a.dHi[1]);
     }
 }
 
@@ -91,47 +102,56 @@ __device__ __forceinline__ uint32_t offset_bits(const OffsetSeg *__restrict__ se
 
 template <bool PRECHECK>
 __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const Row &rm1, const Row &r0, const Row &rp1, const Row &rp2,
-                                          const Row &rp3, uint32_t kbias, const uint8_t *__restrict__ lut, uint32_t &scores_packed) {
-    // centre thresholds, per 16-bit lane: 0x8000 - (diff + 1) -/+ centre
-    const uint32_t kbE = kbias - r0.E1, kbO = kbias - r0.O1;
-    const uint32_t kdE = kbias + r0.E1, kdO = kbias + r0.O1;
-    Acc a = {0u, 0u, 0u, 0u};
+                                          const Row &rp3, __half2 diff2, const uint8_t *__restrict__ lut, uint32_t &scores_packed) {
+    // centre thresholds: nhi = -(centre + diff), lo = centre - diff (the +1024 of every operand cancels)
+    const __half2 c01 = pair<0>(r0), c23 = pair<2>(r0);
+    const __half2 nhi[2] = {__hneg2(__hadd2(c01, diff2)), __hneg2(__hadd2(c23, diff2))};
+    const __half2 lo[2] = {__hsub2(c01, diff2), __hsub2(c23, diff2)};
+    const __half2 k1024 = h2(0x64006400u);
+    Acc a = {{k1024, k1024}, {k1024, k1024}, {k1024, k1024}, {k1024, k1024}};
     // ring index: {dx, dy} per fast.cpp:7-8 -- 0 top, clockwise
-    ring_step<4, 3>(r0, kbE, kbO, kdE, kdO, a);
-    ring_step<8, 0>(rp3, kbE, kbO, kdE, kdO, a);
-    ring_step<12, -3>(r0, kbE, kbO, kdE, kdO, a);
+    ring_step<4, 3>(r0, nhi, lo, a);
+    ring_step<8, 0>(rp3, nhi, lo, a);
+    ring_step<12, -3>(r0, nhi, lo, a);
     uint32_t pass = 0xFFFFFFFFu;
     if (PRECHECK) {
-        // closed form of fast.cpp:20-42: right, bottom, left all brighter or all darker
-        const uint32_t pb = (a.bLo >> 4) & a.bHi & (a.bHi >> 4) & 0x01010101u;
-        const uint32_t pd = (a.dLo >> 4) & a.dHi & (a.dHi >> 4) & 0x01010101u;
-        pass = (pb | pd) * 0xFFu;  // 0xFF per passing pixel
+        // closed form of fast.cpp:20-42: right (bit 4), bottom (bit 8), left (bit 12) all brighter or all darker
+        uint32_t m[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t bl = u32(a.bLo[q]), bh = u32(a.bHi[q]), dl = u32(a.dLo[q]), dh = u32(a.dHi[q]);
+            const uint32_t pb = (bl >> 4) & bh & (bh >> 4) & 0x00010001u;
+            const uint32_t pd = (dl >> 4) & dh & (dh >> 4) & 0x00010001u;
+            m[q] = (pb | pd) * 0xFFu;  // 0x00FF per passing pixel of the pair
+        }
+        pass = prmt(m[0], m[1], 0x6420u);
         if (!__any_sync(0xffffffffu, pass != 0u)) {
             scores_packed = 0u;
             return;
         }
     }
-    ring_step<0, 0>(rm3, kbE, kbO, kdE, kdO, a);
-    ring_step<1, 1>(rm3, kbE, kbO, kdE, kdO, a);
-    ring_step<2, 2>(rm2, kbE, kbO, kdE, kdO, a);
-    ring_step<3, 3>(rm1, kbE, kbO, kdE, kdO, a);
-    ring_step<5, 3>(rp1, kbE, kbO, kdE, kdO, a);
-    ring_step<6, 2>(rp2, kbE, kbO, kdE, kdO, a);
-    ring_step<7, 1>(rp3, kbE, kbO, kdE, kdO, a);
-    ring_step<9, -1>(rp3, kbE, kbO, kdE, kdO, a);
-    ring_step<10, -2>(rp2, kbE, kbO, kdE, kdO, a);
-    ring_step<11, -3>(rp1, kbE, kbO, kdE, kdO, a);
-    ring_step<13, -3>(rm1, kbE, kbO, kdE, kdO, a);
-    ring_step<14, -2>(rm2, kbE, kbO, kdE, kdO, a);
-    ring_step<15, -1>(rm3, kbE, kbO, kdE, kdO, a);
+    ring_step<0, 0>(rm3, nhi, lo, a);
+    ring_step<1, 1>(rm3, nhi, lo, a);
+    ring_step<2, 2>(rm2, nhi, lo, a);
+    ring_step<3, 3>(rm1, nhi, lo, a);
+    ring_step<5, 3>(rp1, nhi, lo, a);
+    ring_step<6, 2>(rp2, nhi, lo, a);
+    ring_step<7, 1>(rp3, nhi, lo, a);
+    ring_step<9, -1>(rp3, nhi, lo, a);
+    ring_step<10, -2>(rp2, nhi, lo, a);
+    ring_step<11, -3>(rp1, nhi, lo, a);
+    ring_step<13, -3>(rm1, nhi, lo, a);
+    ring_step<14, -2>(rm2, nhi, lo, a);
+    ring_step<15, -1>(rm3, nhi, lo, a);
 
     uint32_t sp = 0u;
-    if ((a.bLo | a.bHi | a.dLo | a.dHi) != 0u) {
+    const uint32_t any = u32(a.bLo[0]) | u32(a.bLo[1]) | u32(a.bHi[0]) | u32(a.bHi[1]) | u32(a.dLo[0]) | u32(a.dLo[1]) | u32(a.dHi[0]) | u32(a.dHi[1]);
+    if (any != 0x64006400u) {
         // per pixel: 16-bit masks -> longest circular run (fast.cpp:55-78), best of both polarities
-        const uint32_t b0 = prmt(a.bLo, a.bHi, 0x4440u) & 0xFFFFu, d0 = prmt(a.dLo, a.dHi, 0x4440u) & 0xFFFFu;
-        const uint32_t b1 = prmt(a.bLo, a.bHi, 0x4451u) & 0xFFFFu, d1 = prmt(a.dLo, a.dHi, 0x4451u) & 0xFFFFu;
-        const uint32_t b2 = prmt(a.bLo, a.bHi, 0x4462u) & 0xFFFFu, d2 = prmt(a.dLo, a.dHi, 0x4462u) & 0xFFFFu;
-        const uint32_t b3 = prmt(a.bLo, a.bHi, 0x4473u) & 0xFFFFu, d3 = prmt(a.dLo, a.dHi, 0x4473u) & 0xFFFFu;
+        const uint32_t b0 = prmt(u32(a.bLo[0]), u32(a.bHi[0]), 0x7740u) & 0xFFFFu, d0 = prmt(u32(a.dLo[0]), u32(a.dHi[0]), 0x7740u) & 0xFFFFu;
+        const uint32_t b1 = prmt(u32(a.bLo[0]), u32(a.bHi[0]), 0x7762u) & 0xFFFFu, d1 = prmt(u32(a.dLo[0]), u32(a.dHi[0]), 0x7762u) & 0xFFFFu;
+        const uint32_t b2 = prmt(u32(a.bLo[1]), u32(a.bHi[1]), 0x7740u) & 0xFFFFu, d2 = prmt(u32(a.dLo[1]), u32(a.dHi[1]), 0x7740u) & 0xFFFFu;
+        const uint32_t b3 = prmt(u32(a.bLo[1]), u32(a.bHi[1]), 0x7762u) & 0xFFFFu, d3 = prmt(u32(a.dLo[1]), u32(a.dHi[1]), 0x7762u) & 0xFFFFu;
         const uint32_t s0 = max((uint32_t)lut[b0], (uint32_t)lut[d0]);
         const uint32_t s1 = max((uint32_t)lut[b1], (uint32_t)lut[d1]);
         const uint32_t s2 = max((uint32_t)lut[b2], (uint32_t)lut[d2]);
@@ -141,11 +161,13 @@ __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const 
     scores_packed = sp & pass;
 }
 
-template <bool PRECHECK>
-__global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p) {
+template <bool PRECHECK, bool SCORE_MAP>
+__global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(const FastArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *lut = smem;                                               // 65536 B: run-length table
-    OffsetSeg *segs = reinterpret_cast<OffsetSeg *>(smem + 65536);     // p.n_seg + 1 entries
+    OffsetSeg *segs = reinterpret_cast<OffsetSeg *>(smem + 65536);     // p.n_seg + 1 entries (at most FAST_MAX_SEGS)
+    // per-warp staging buffer for candidate keys: one global atomic per flush instead of one per row
+    uint64_t *stage = reinterpret_cast<uint64_t *>(smem + 65536 + FAST_MAX_SEGS * sizeof(OffsetSeg)) + (threadIdx.x >> 5) * FAST_STAGE_KEYS;
     for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(lut)[i] = __ldg(reinterpret_cast<const uint4 *>(p.lut) + i);
     for (int i = threadIdx.x; i <= p.n_seg; i += blockDim.x) segs[i] = p.segs[i];
     __syncthreads();
@@ -155,8 +177,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
     const int warps_per_block = blockDim.x >> 5;
     const int64_t total_warps = int64_t(gridDim.x) * warps_per_block;
     const int64_t gwarp = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
-    const uint32_t kbias = (0x8000u - uint32_t(p.diff) - 1u) * 0x00010001u;
+    const __half2 diff2 = __float2half2_rn(float(p.diff));
     const int inner_cols = fv.cols - 6;
+    const int last_row = fv.rows - 1;
 
     for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
         // item -> (frame, band, strip); strips fastest so neighbouring warps share L1 lines
@@ -168,28 +191,25 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
         const int row_end = min(row_begin + p.band_rows, fv.rows - 3);
         if (row_begin >= row_end) continue;
 
-        // Rows are read as three aligned words per lane.  Addresses are clamped instead of predicated: a
-        // clamped word only ever feeds pixels outside the interior, whose results are masked below.
+        // Rows are read as three aligned words per lane through three running pointers.  Addresses are clamped
+        // instead of predicated: a clamped word only ever feeds pixels outside the interior, whose results are
+        // masked below, and a clamped row only feeds rows past the band's end, which are dropped.
         const int w = strip * 32 + lane;                                // this lane's word in the row
-        const int wl = min(max(w - 1, 0), fv.words_per_row - 1) * 4;
-        const int wc = min(w, fv.words_per_row - 1) * 4;
-        const int wr = min(w + 1, fv.words_per_row - 1) * 4;
-        const uint8_t *fbase = fv.data + int64_t(frame) * fv.frame_stride;
-        const int last_row = fv.rows - 1;
-#define FD_LOAD_ROW(ROW, W0, W1, W2)                                          \
-        {                                                                     \
-            const uint8_t *rp__ = fbase + int64_t(min(ROW, last_row)) * fv.pitch; \
-            W0 = ld_word(rp__ + wl);                                          \
-            W1 = ld_word(rp__ + wc);                                          \
-            W2 = ld_word(rp__ + wr);                                          \
-        }
+        const uint8_t *fbase = fv.data + int64_t(frame) * fv.frame_stride + int64_t(row_begin - 3) * fv.pitch;
+        const uint8_t *pl = fbase + min(max(w - 1, 0), fv.words_per_row - 1) * 4;
+        const uint8_t *pc = fbase + min(w, fv.words_per_row - 1) * 4;
+        const uint8_t *pr = fbase + min(w + 1, fv.words_per_row - 1) * 4;
+        int next_row = row_begin - 3;  // the row the pointers address
 
         Row rw[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
-            uint32_t w0, w1, w2;
-            FD_LOAD_ROW(row_begin - 3 + i, w0, w1, w2);
-            make_row(rw[i], w0, w1, w2);
+            make_row(rw[i], ld_word(pl), ld_word(pc), ld_word(pr));
+            const int64_t adv = (next_row < last_row) ? fv.pitch : 0;
+            pl += adv;
+            pc += adv;
+            pr += adv;
+            ++next_row;
         }
 
         const int col0 = 4 * w;
@@ -208,40 +228,56 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
             int s_need = 17;
             for (int sc = 16; sc >= 0; --sc)
                 if (__fadd_rn(float(sc), off_hi) > p.thr) s_need = sc;
-            need_add = (s_need == 0) ? 0x80808080u : (s_need > 16 ? 0u : (0x80u - uint32_t(s_need)) * 0x01010101u);
+            need_add = (s_need > 16) ? 0u : (0x80u - uint32_t(s_need)) * 0x01010101u;
         }
-        uint8_t *score_base = p.score_map ? p.score_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
+        int seg = 0;                // linear piece of the offset table that holds the first pixel of the current row group
+        uint32_t n_staged = 0u;     // warp-uniform fill of the staging buffer
+        uint32_t *counter = p.cand_counts + frame;
+        uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
+        uint8_t *score_ptr = nullptr;
+        if (SCORE_MAP) score_ptr = p.score_map + (int64_t(frame) * fv.rows + row_begin) * fv.cols + col0;
 
         for (int row = row_begin; row < row_end; row += 7) {
             uint32_t spv[7];
             uint32_t hits = 0u;  // warp-uniform: phases with at least one possible candidate
 #pragma unroll
             for (int ph = 0; ph < 7; ++ph) {
-                const int r = row + ph;
-                uint32_t n0, n1, n2;
-                FD_LOAD_ROW(r + 4, n0, n1, n2);  // the row that enters the window next step
+                // the row that enters the window next step (row + ph + 4)
+                const uint32_t n0 = ld_word(pl), n1 = ld_word(pc), n2 = ld_word(pr);
+                const int64_t adv = (next_row < last_row) ? fv.pitch : 0;
+                pl += adv;
+                pc += adv;
+                pr += adv;
+                ++next_row;
                 uint32_t sp;
                 fast_step<PRECHECK>(rw[(ph + 0) % 7], rw[(ph + 1) % 7], rw[(ph + 2) % 7], rw[(ph + 3) % 7], rw[(ph + 4) % 7],
-                                    rw[(ph + 5) % 7], rw[(ph + 6) % 7], kbias, lut, sp);
+                                    rw[(ph + 5) % 7], rw[(ph + 6) % 7], diff2, lut, sp);
                 sp &= col_ok;
-                const bool live = r < row_end;  // rows past the band are computed on clamped data and dropped
-                if (score_base != nullptr && live && col0 < fv.cols) {
-                    uint8_t *dst = score_base + int64_t(r) * fv.cols + col0;
-                    if (p.score_aligned && col0 + 3 < fv.cols) {
-                        *reinterpret_cast<uint32_t *>(dst) = sp;
-                    } else {
+                const bool live = row + ph < row_end;  // rows past the band are computed on clamped data and dropped
+                if (SCORE_MAP) {
+                    if (live && col0 < fv.cols) {
+                        if (p.score_aligned && col0 + 3 < fv.cols) {
+                            *reinterpret_cast<uint32_t *>(score_ptr) = sp;
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (col0 + j < fv.cols) dst[j] = uint8_t(sp >> (8 * j));
+                            for (int j = 0; j < 4; ++j)
+                                if (col0 + j < fv.cols) score_ptr[j] = uint8_t(sp >> (8 * j));
+                        }
                     }
+                    score_ptr += fv.cols;
                 }
                 spv[ph] = sp;
-                const bool hit = live && ((((sp + need_add) | (need_add & 0x80808080u)) & col_ok & 0x80808080u) != 0u);
+                const bool hit = live && (((sp + need_add) & col_ok & 0x80808080u) != 0u);
                 if (__any_sync(0xffffffffu, hit)) hits |= 1u << ph;
                 make_row(rw[(ph + 0) % 7], n0, n1, n2);
             }
             // response = score + offset(k), k = index of the pixel among the masked-in interior pixels in raster
-            // order (fast.cpp:85-93); candidates are appended with one atomic per warp and row.
+            // order (fast.cpp:85-93).  Only rows flagged above get here, and only pixels whose score can reach the
+            // threshold do the float work.  Candidates go to the warp's staging buffer.
+            if (hits != 0u) {
+                const uint32_t k_group = uint32_t(row - 3) * uint32_t(inner_cols);
+                while (k_group >= segs[seg + 1].k_start) ++seg;  // warp-uniform, monotonic over the band
+            }
             while (hits != 0u) {
                 const int ph = __ffs(hits) - 1;
                 hits &= hits - 1u;
@@ -249,14 +285,22 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
 #pragma unroll
                 for (int q = 1; q < 7; ++q) sp = (ph == q) ? spv[q] : sp;
                 const int r = row + ph;
+                const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels whose score can reach the threshold at all
+                const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
+                const uint32_t k_lo = k_row + uint32_t(max(col0 - 3, 0));  // <= k of every interior pixel of this lane
+                int sg = seg;
+                if (able != 0u)
+                    while (k_lo >= segs[sg + 1].k_start) ++sg;
                 uint32_t mine = 0u;
                 float resp[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     resp[j] = 0.0f;
-                    if ((col_ok >> (8 * j)) & 1u) {
-                        const uint32_t k = uint32_t(r - 3) * uint32_t(inner_cols) + uint32_t(col0 + j - 3);
-                        const float off = __uint_as_float(offset_bits(segs, p.n_seg, k));
+                    if ((able >> (8 * j + 7)) & 1u) {
+                        const uint32_t k = k_row + uint32_t(col0 + j - 3);
+                        int sj = sg;
+                        while (k >= segs[sj + 1].k_start) ++sj;
+                        const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
                         const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);
                         if (v > p.thr) {
                             resp[j] = v;
@@ -264,40 +308,59 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs p)
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, mine != 0u)) {
-                    uint32_t pos = warp_reserve(p.cand_counts + frame, __popc(mine));
-                    uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
+                // warp-local append: ballots give every candidate its place without shuffles or atomics
+                uint32_t base = n_staged;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if ((mine >> j) & 1u) {
-                            if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[j], uint32_t(r) * uint32_t(fv.cols) + uint32_t(col0 + j));
-                            ++pos;
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+                    if ((mine >> j) & 1u) stage[base + __popc(m & ((1u << lane) - 1u))] = make_cand_key(resp[j], uint32_t(r), uint32_t(col0 + j));
+                    base += __popc(m);
+                }
+                n_staged = base;
+                if (n_staged > FAST_STAGE_KEYS - 128) {  // a row adds at most 128 keys
+                    __syncwarp();
+                    uint32_t g = 0u;
+                    if (lane == 0) g = atomicAdd(counter, n_staged);
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    for (uint32_t i = lane; i < n_staged; i += 32)
+                        if (g + i < p.cand_capacity) slot[g + i] = stage[i];
+                    __syncwarp();
+                    n_staged = 0u;
                 }
             }
         }
-#undef FD_LOAD_ROW
+        if (n_staged != 0u) {  // flush what the band left behind
+            __syncwarp();
+            uint32_t g = 0u;
+            if (lane == 0) g = atomicAdd(counter, n_staged);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            for (uint32_t i = lane; i < n_staged; i += 32)
+                if (g + i < p.cand_capacity) slot[g + i] = stage[i];
+            __syncwarp();
+        }
     }
 }
 
 }  // namespace
 
-size_t fast_smem_bytes(int n_seg) { return 65536 + sizeof(OffsetSeg) * size_t(n_seg + 1); }
+size_t fast_smem_bytes(int n_seg) {
+    (void)n_seg;
+    return 65536 + FAST_MAX_SEGS * sizeof(OffsetSeg) + size_t(FAST_THREADS / 32) * FAST_STAGE_KEYS * 8;
+}
+
+template <bool PRECHECK, bool SCORE_MAP>
+static cudaError_t launch_fast_t(const FastArgs &args, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(fast_kernel<PRECHECK, SCORE_MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    fast_kernel<PRECHECK, SCORE_MAP><<<grid, FAST_THREADS, smem, stream>>>(args);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes(args.n_seg);
-    cudaError_t e;
-    if (precheck) {
-        e = cudaFuncSetAttribute(fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        fast_kernel<true><<<grid, FAST_THREADS, smem, stream>>>(args);
-    } else {
-        e = cudaFuncSetAttribute(fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        fast_kernel<false><<<grid, FAST_THREADS, smem, stream>>>(args);
-    }
-    return cudaGetLastError();
+    const bool sm = args.score_map != nullptr;
+    if (precheck) return sm ? launch_fast_t<true, true>(args, grid, smem, stream) : launch_fast_t<true, false>(args, grid, smem, stream);
+    return sm ? launch_fast_t<false, true>(args, grid, smem, stream) : launch_fast_t<false, false>(args, grid, smem, stream);
 }
 
 }  // namespace fdb

@@ -7,6 +7,9 @@ namespace fdb {
 
 // ---- kernel 2: FAST --------------------------------------------------------------------------
 constexpr int FAST_THREADS = 256;
+constexpr int FAST_CTAS_PER_SM = 2;
+constexpr int FAST_MAX_SEGS = 96;     // linear pieces of the offset table kept in shared memory (incl. sentinel)
+constexpr int FAST_STAGE_KEYS = 256;  // per-warp candidate staging buffer
 
 // One linear piece of the reference's running float offset (fast.cpp:85,93): for masked-in pixel
 // index k in [k_start, next.k_start) the offset's BIT PATTERN is bits_start + (k - k_start) * step.
@@ -52,12 +55,13 @@ struct CornerArgs {
 cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream);
 
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
-constexpr int SELECT_THREADS = 512;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
+constexpr int GREEDY_WARPS = 4;           // one warp per frame
 
 struct SelectArgs {
     int rows, cols, n_frames;
     uint64_t *cand_keys;            // in: unsorted; out: sorted ascending (= response descending, raster ties)
-    uint64_t *cand_scratch;         // same size, for the out-of-shared-memory sort path
     const uint32_t *cand_counts;
     uint32_t cand_capacity;
     int min_distance;
@@ -68,11 +72,10 @@ struct SelectArgs {
     int kp_capacity;
     uint32_t *cell_scratch;         // global fallback for the accepted-point cell grid (per frame), may be null
     int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
+    uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
-    int smem_sort_capacity;         // keys that fit the shared-memory sort
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
 };
-size_t select_smem_bytes(const SelectArgs &a);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
 
 // ---- kernel 4: steered BRIEF --------------------------------------------------------------------
@@ -100,11 +103,11 @@ struct LsdArgs {
 };
 cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
 // Sort each frame's seed keys ascending and strip them to int32 map indices.
-cudaError_t launch_seed_sort(uint64_t *keys, uint64_t *scratch, const uint32_t *counts, int64_t slot, int n_frames, int32_t *sorted_idx,
-                             int map_rows, int map_cols, cudaStream_t stream);
+cudaError_t launch_seed_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_frames, int32_t *sorted_idx, int map_cols,
+                             cudaStream_t stream);
 
 // ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
-cudaError_t launch_segment_sort(uint64_t *keys, uint64_t *scratch, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity,
+cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity, uint32_t *overflow_flag,
                                 cudaStream_t stream);
 
 // ---- mask from pre-existing features ------------------------------------------------------------
