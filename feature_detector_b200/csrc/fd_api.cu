@@ -32,10 +32,11 @@ struct fd_context {
 
     DevBuf lut;       // 65536 B
     DevBuf segs;      // OffsetSeg table
+    std::vector<OffsetSeg> host_segs;
     int n_seg = 0;
     uint32_t seg_count_covered = 0;
 
-    DevBuf keys, keys_scratch, counts, flags, cells;
+    DevBuf keys, keys_scratch, counts, flags, cells, alive, kept;
     uint32_t cand_capacity = 0;
     bool have_candidates = false, candidates_sorted = false;
 
@@ -164,6 +165,40 @@ std::vector<OffsetSeg> build_offset_table(uint32_t count) {
     return segs;
 }
 
+// Offset bit pattern at pixel index k from the host copy of the table.
+uint32_t host_offset_bits(const std::vector<OffsetSeg> &segs, uint32_t k) {
+    size_t lo = 0, hi = segs.size() - 2;
+    while (lo < hi) {
+        const size_t mid = (lo + hi + 1) / 2;
+        if (segs[mid].k_start <= k) lo = mid; else hi = mid - 1;
+    }
+    return segs[lo].bits_start + (k - segs[lo].k_start) * segs[lo].step;
+}
+
+// kmin[s] = smallest pixel index k in [0, count) with fl(float(s) + offset(k)) > thr, else 0xFFFFFFFF.
+// fl(s + offset) is non-decreasing in k because the offset is, so a binary search finds it.
+void build_kmin(const std::vector<OffsetSeg> &segs, uint32_t count, float thr, uint32_t kmin[17]) {
+    for (int s = 0; s <= 16; ++s) {
+        auto passes = [&](uint32_t k) {
+            const uint32_t b = host_offset_bits(segs, k);
+            float off;
+            std::memcpy(&off, &b, 4);
+            volatile float v = float(s) + off;  // one rounding, like fast.cpp:89
+            return v > thr;
+        };
+        if (count == 0 || !passes(count - 1)) {
+            kmin[s] = 0xFFFFFFFFu;
+            continue;
+        }
+        uint32_t lo = 0, hi = count - 1;  // passes(hi) holds
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (passes(mid)) hi = mid; else lo = mid + 1;
+        }
+        kmin[s] = lo;
+    }
+}
+
 fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
     if (ctx->lut.ptr == nullptr) {
         const std::vector<uint8_t> lut = build_run_lut();
@@ -179,6 +214,7 @@ fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
         FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (segs.size() > size_t(FAST_MAX_SEGS)) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "FAST offset table has too many pieces for this frame size");
         ctx->n_seg = int(segs.size()) - 1;
+        ctx->host_segs = segs;
         ctx->seg_count_covered = want;
     }
     return FD_OK;
@@ -245,6 +281,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.lut = static_cast<const uint8_t *>(ctx->lut.ptr);
             a.segs = static_cast<const OffsetSeg *>(ctx->segs.ptr);
             a.n_seg = ctx->n_seg;
+            build_kmin(ctx->host_segs, interior, p->min_valid_response, a.kmin);
             a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
             a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
             a.cand_capacity = cap;
@@ -252,7 +289,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
             int grid;
-            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, 2, 14, 7, a.band_rows, a.n_bands, a.n_items, grid);
+            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 7, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
             ++ctx->launches;
         }
@@ -308,15 +345,20 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     a.cells_y = (fv.rows + cell - 1) / cell;
     const size_t cell_bytes = size_t(a.cells_x) * a.cells_y * 4;
     a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
-    a.cells_in_smem = cell_bytes <= 16 * 1024;
+    a.cells_in_smem = cell_bytes * 3 <= 24 * 1024;
     if (!a.cells_in_smem) {
-        FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
+        FD_TRY(reserve(ctx, ctx->cells, cell_bytes * 3 * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
+    a.kept_capacity = a.cells_x * a.cells_y;
+    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * ctx->cand_capacity));
+    FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
+    a.alive_scratch = static_cast<uint8_t *>(ctx->alive.ptr);
+    a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     FD_CUDA(ctx, launch_select(a, ctx->stream));
-    ctx->launches += 2;
-    ctx->candidates_sorted = true;
+    ++ctx->launches;
+    ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
     return FD_OK;
 }
@@ -360,7 +402,7 @@ fd_status fd_destroy(fd_context *ctx) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->kp,
+    for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
                       &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted})
         release(*b);

@@ -218,18 +218,10 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
         for (int j = 0; j < 4; ++j)
             if (col0 + j >= 3 && col0 + j <= fv.cols - 4) col_ok |= 0xFFu << (8 * j);
 
-        // Smallest score that can become a candidate anywhere in this band: the offset only grows with k, so
-        // fl(score + offset) <= fl(score + offset at the band's last pixel).  Rows whose scores all stay below it
-        // skip the float path entirely (with the demo threshold 10 that is almost every row).
-        uint32_t need_add;  // adding it to the packed scores sets bit 7 of every byte whose score >= s_need
-        {
-            const uint32_t k_hi = uint32_t(row_end - 1 - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
-            const float off_hi = __uint_as_float(offset_bits(segs, p.n_seg, k_hi));
-            int s_need = 17;
-            for (int sc = 16; sc >= 0; --sc)
-                if (__fadd_rn(float(sc), off_hi) > p.thr) s_need = sc;
-            need_add = (s_need > 16) ? 0u : (0x80u - uint32_t(s_need)) * 0x01010101u;
-        }
+        // p.kmin[s] = first pixel index k at which fl(s + offset(k)) > threshold (host-computed from the same table;
+        // non-increasing in s).  s_last / s_first = smallest score that makes a candidate at the last / first pixel
+        // of the current group of 7 rows; both only move down as k grows.
+        int s_last = 17, s_first = 17;
         int seg = 0;                // linear piece of the offset table that holds the first pixel of the current row group
         uint32_t n_staged = 0u;     // warp-uniform fill of the staging buffer
         uint32_t *counter = p.cand_counts + frame;
@@ -238,6 +230,14 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
         if (SCORE_MAP) score_ptr = p.score_map + (int64_t(frame) * fv.rows + row_begin) * fv.cols + col0;
 
         for (int row = row_begin; row < row_end; row += 7) {
+            {
+                const uint32_t k_first = uint32_t(row - 3) * uint32_t(inner_cols);
+                const uint32_t k_last = uint32_t(min(row + 6, row_end - 1) - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
+                while (s_last > 0 && p.kmin[s_last - 1] <= k_last) --s_last;
+                while (s_first > 0 && p.kmin[s_first - 1] <= k_first) --s_first;
+            }
+            // adding need_add to the packed scores sets bit 7 of every byte whose score >= s_last
+            const uint32_t need_add = (s_last > 16) ? 0u : (0x80u - uint32_t(s_last)) * 0x01010101u;
             uint32_t spv[7];
             uint32_t hits = 0u;  // warp-uniform: phases with at least one possible candidate
 #pragma unroll
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
 #pragma unroll
                 for (int q = 1; q < 7; ++q) sp = (ph == q) ? spv[q] : sp;
                 const int r = row + ph;
-                const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels whose score can reach the threshold at all
+                const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels with score >= s_last
                 const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
                 const uint32_t k_lo = k_row + uint32_t(max(col0 - 3, 0));  // <= k of every interior pixel of this lane
                 int sg = seg;
@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
                         while (k >= segs[sj + 1].k_start) ++sj;
                         const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
                         const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);
-                        if (v > p.thr) {
+                        // inside a group whose first and last pixel need the same score the byte test above is already
+                        // exact; otherwise the group straddles a threshold crossing and the float test decides
+                        if (s_first == s_last || v > p.thr) {
                             resp[j] = v;
                             mine |= 1u << j;
                         }

@@ -24,6 +24,7 @@ struct FastArgs {
     const uint8_t *lut;       // 65536-entry longest-circular-run table (device)
     const OffsetSeg *segs;    // n_seg pieces + one sentinel (k_start = 0xFFFFFFFF)
     int n_seg;
+    uint32_t kmin[17];        // first pixel index at which score s yields response > thr (0xFFFFFFFF = never)
     uint64_t *cand_keys;      // n_frames slots of cand_capacity keys
     uint32_t *cand_counts;    // n_frames
     uint32_t cand_capacity;
@@ -57,7 +58,8 @@ cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream)
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
-constexpr int GREEDY_WARPS = 4;           // one warp per frame
+constexpr int SELECT_THREADS = 256;
+constexpr int SELECT_SORT_SMEM = 1024;    // kept points sorted in shared memory up to this many
 
 struct SelectArgs {
     int rows, cols, n_frames;
@@ -70,7 +72,10 @@ struct SelectArgs {
     float4 *keypoints;              // n_frames slots of kp_capacity (x, y, response, 0)
     int32_t *kp_counts;
     int kp_capacity;
-    uint32_t *cell_scratch;         // global fallback for the accepted-point cell grid (per frame), may be null
+    uint8_t *alive_scratch;         // n_frames * cand_capacity liveness flags
+    uint64_t *kept_keys;            // n_frames slots of kept_capacity keys (the kept set before the cut)
+    int kept_capacity;              // = number of grid cells (at most one kept point per cell)
+    uint32_t *cell_scratch;         // global fallback for the three per-cell arrays (3 * cells per frame), may be null
     int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
     uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
