@@ -289,7 +289,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
             int grid;
-            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 7, a.band_rows, a.n_bands, a.n_items, grid);
+            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
             ++ctx->launches;
         }

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t offset_bits(const OffsetSeg *__restrict__ se
 
 template <bool PRECHECK>
 __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const Row &rm1, const Row &r0, const Row &rp1, const Row &rp2,
-                                          const Row &rp3, __half2 diff2, const uint8_t *__restrict__ lut, uint32_t &scores_packed) {
+                                          const Row &rp3, __half2 diff2, const uint8_t *__restrict__ lut, int prune, uint32_t &scores_packed) {
     // centre thresholds: nhi = -(centre + diff), lo = centre - diff (the +1024 of every operand cancels)
     const __half2 c01 = pair<0>(r0), c23 = pair<2>(r0);
     const __half2 nhi[2] = {__hneg2(__hadd2(c01, diff2)), __hneg2(__hadd2(c23, diff2))};
@@ -131,6 +131,29 @@ __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const 
         }
     }
     ring_step<0, 0>(rm3, nhi, lo, a);
+    if (prune != 0) {
+        // Threshold-aware pruning (exact): only scores >= s_min can become candidates in this row group, and a
+        // circular run of s_min ring pixels contains floor(s_min / 4) CONSECUTIVE compass positions (0, 4, 8, 12)
+        // of the same polarity.  prune = 1: s_min in 4..7 (one compass flag); prune = 2: s_min >= 8 (two adjacent).
+        // A warp whose 128 pixels all fail cannot hold a candidate and skips the other 12 ring positions.
+        uint32_t ok = 0u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            // compass flags per pixel: bit 0 = pos 0, bit 4 = pos 4, bit 1 = pos 8, bit 5 = pos 12
+            const uint32_t xb = (u32(a.bLo[q]) & 0x00110011u) | ((u32(a.bHi[q]) & 0x00110011u) << 1);
+            const uint32_t xd = (u32(a.dLo[q]) & 0x00110011u) | ((u32(a.dHi[q]) & 0x00110011u) << 1);
+            if (prune == 1) {
+                ok |= xb | xd;
+            } else {
+                ok |= (xb & (xb >> 4)) | (xb & (xb >> 3) & 0x00020002u) | (xb & (xb >> 5) & 0x00010001u);
+                ok |= (xd & (xd >> 4)) | (xd & (xd >> 3) & 0x00020002u) | (xd & (xd >> 5) & 0x00010001u);
+            }
+        }
+        if (!__any_sync(0xffffffffu, ok != 0u)) {
+            scores_packed = 0u;
+            return;
+        }
+    }
     ring_step<1, 1>(rm3, nhi, lo, a);
     ring_step<2, 2>(rm2, nhi, lo, a);
     ring_step<3, 3>(rm1, nhi, lo, a);
@@ -229,63 +252,53 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
         uint8_t *score_ptr = nullptr;
         if (SCORE_MAP) score_ptr = p.score_map + (int64_t(frame) * fv.rows + row_begin) * fv.cols + col0;
 
-        for (int row = row_begin; row < row_end; row += 7) {
-            {
+        for (int row = row_begin; row < row_end; ++row) {
+            // The row loop is deliberately NOT unrolled: the seven window rows shift down by register moves instead of
+            // by renaming, which keeps the whole kernel inside the instruction cache (an unrolled-by-7 body does not fit
+            // and stalls on instruction fetch).
+            if (((row - row_begin) % 7) == 0) {
                 const uint32_t k_first = uint32_t(row - 3) * uint32_t(inner_cols);
                 const uint32_t k_last = uint32_t(min(row + 6, row_end - 1) - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
                 while (s_last > 0 && p.kmin[s_last - 1] <= k_last) --s_last;
                 while (s_first > 0 && p.kmin[s_first - 1] <= k_first) --s_first;
+                while (k_first >= segs[seg + 1].k_start) ++seg;  // warp-uniform, monotonic over the band
             }
             // adding need_add to the packed scores sets bit 7 of every byte whose score >= s_last
             const uint32_t need_add = (s_last > 16) ? 0u : (0x80u - uint32_t(s_last)) * 0x01010101u;
-            uint32_t spv[7];
-            uint32_t hits = 0u;  // warp-uniform: phases with at least one possible candidate
+            const int prune = SCORE_MAP ? 0 : (s_last >= 8 ? 2 : (s_last >= 4 ? 1 : 0));
+
+            // the row that enters the window next step (row + 4)
+            const uint32_t n0 = ld_word(pl), n1 = ld_word(pc), n2 = ld_word(pr);
+            const int64_t adv = (next_row < last_row) ? fv.pitch : 0;
+            pl += adv;
+            pc += adv;
+            pr += adv;
+            ++next_row;
+            uint32_t sp;
+            fast_step<PRECHECK>(rw[0], rw[1], rw[2], rw[3], rw[4], rw[5], rw[6], diff2, lut, prune, sp);
+            sp &= col_ok;
+            if (SCORE_MAP) {
+                if (col0 < fv.cols) {
+                    if (p.score_aligned && col0 + 3 < fv.cols) {
+                        *reinterpret_cast<uint32_t *>(score_ptr) = sp;
+                    } else {
 #pragma unroll
-            for (int ph = 0; ph < 7; ++ph) {
-                // the row that enters the window next step (row + ph + 4)
-                const uint32_t n0 = ld_word(pl), n1 = ld_word(pc), n2 = ld_word(pr);
-                const int64_t adv = (next_row < last_row) ? fv.pitch : 0;
-                pl += adv;
-                pc += adv;
-                pr += adv;
-                ++next_row;
-                uint32_t sp;
-                fast_step<PRECHECK>(rw[(ph + 0) % 7], rw[(ph + 1) % 7], rw[(ph + 2) % 7], rw[(ph + 3) % 7], rw[(ph + 4) % 7],
-                                    rw[(ph + 5) % 7], rw[(ph + 6) % 7], diff2, lut, sp);
-                sp &= col_ok;
-                const bool live = row + ph < row_end;  // rows past the band are computed on clamped data and dropped
-                if (SCORE_MAP) {
-                    if (live && col0 < fv.cols) {
-                        if (p.score_aligned && col0 + 3 < fv.cols) {
-                            *reinterpret_cast<uint32_t *>(score_ptr) = sp;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col0 + j < fv.cols) score_ptr[j] = uint8_t(sp >> (8 * j));
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if (col0 + j < fv.cols) score_ptr[j] = uint8_t(sp >> (8 * j));
                     }
-                    score_ptr += fv.cols;
                 }
-                spv[ph] = sp;
-                const bool hit = live && (((sp + need_add) & col_ok & 0x80808080u) != 0u);
-                if (__any_sync(0xffffffffu, hit)) hits |= 1u << ph;
-                make_row(rw[(ph + 0) % 7], n0, n1, n2);
+                score_ptr += fv.cols;
             }
-            // response = score + offset(k), k = index of the pixel among the masked-in interior pixels in raster
-            // order (fast.cpp:85-93).  Only rows flagged above get here, and only pixels whose score can reach the
-            // threshold do the float work.  Candidates go to the warp's staging buffer.
-            if (hits != 0u) {
-                const uint32_t k_group = uint32_t(row - 3) * uint32_t(inner_cols);
-                while (k_group >= segs[seg + 1].k_start) ++seg;  // warp-uniform, monotonic over the band
-            }
-            while (hits != 0u) {
-                const int ph = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                uint32_t sp = spv[0];
 #pragma unroll
-                for (int q = 1; q < 7; ++q) sp = (ph == q) ? spv[q] : sp;
-                const int r = row + ph;
-                const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels with score >= s_last
+            for (int i = 0; i < 6; ++i) rw[i] = rw[i + 1];
+            make_row(rw[6], n0, n1, n2);
+
+            // response = score + offset(k), k = index of the pixel among the masked-in interior pixels in raster
+            // order (fast.cpp:85-93).  Only rows holding a pixel whose score can reach the threshold get here, and
+            // only those pixels do the float work.  Candidates go to the warp's staging buffer.
+            const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels with score >= s_last
+            if (__any_sync(0xffffffffu, able != 0u)) {
+                const int r = row;
                 const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
                 const uint32_t k_lo = k_row + uint32_t(max(col0 - 3, 0));  // <= k of every interior pixel of this lane
                 int sg = seg;
