@@ -1,0 +1,101 @@
+// GPU replacement for FeatureLineDetector::ComputeLineLevelAngleMap
+// (reference src/feature_line_detector/feature_line_detector.cpp:56-97).
+//
+// The reference's line detector keeps region growing, rectangle fitting and validation (:99-228) in host code, and the
+// north star leaves them there.  What moves to the GPU is the dense stage: the 2x2 gradient, its norm, the validity
+// test, the level-line angle and the ordering of the valid pixels by norm (kernel 5, csrc/fd_lsd.cu).  This class runs
+// that stage and then leaves the host stage's input exactly as ComputeLineLevelAngleMap would have left it:
+// FillPixelParams() writes the reference's column-major PixelParam matrix and its sorted pointer list, so the body of
+// ComputeLineLevelAngleMap in a reference checkout becomes the two calls shown in INTEGRATION.md.
+#ifndef FD_B200_FEATURE_LINE_FIELD_H_
+#define FD_B200_FEATURE_LINE_FIELD_H_
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "basic_type.h"
+#include "datatype_image.h"
+
+struct fd_context;
+
+namespace feature_detector {
+
+class LineLevelAngleField {
+public:
+    struct Options {
+        float kMinValidGradientNorm = 20.0f;  // feature_line_detector.h:41
+    };
+
+    LineLevelAngleField() = default;
+    ~LineLevelAngleField();
+    LineLevelAngleField(const LineLevelAngleField &) = delete;
+    LineLevelAngleField &operator=(const LineLevelAngleField &) = delete;
+
+    Options &options() { return options_; }
+    const Options &options() const { return options_; }
+
+    // false for a null image or rows / cols < 2 (feature_line_detector.cpp:14), or when the GPU call fails.
+    bool Compute(const GrayImage &image);
+
+    // Results of the last Compute: maps are image_rows x image_cols floats, row-major (last row / column zero);
+    // seeds are row * image_cols + col of the valid pixels, norm descending, ties in the reference's push order.
+    int32_t image_rows() const { return rows_; }
+    int32_t image_cols() const { return cols_; }
+    const std::vector<float> &gradient_norm() const { return norm_; }
+    const std::vector<float> &line_level_angle() const { return angle_; }
+    const std::vector<int32_t> &sorted_seeds() const { return seeds_; }
+
+    // Leave `pixels` (Eigen::Matrix<PixelParam, Dynamic, Dynamic>) and `sorted` (std::vector<PixelParam *>) as the
+    // reference's ComputeLineLevelAngleMap leaves pixels_ and sorted_pixels_, including what it does NOT touch:
+    // a resize to an unchanged size keeps old flags, invalid pixels keep their old angle, and `sorted` is appended to.
+    template <typename PixelMatrix, typename PixelPtrVector>
+    void FillPixelParams(PixelMatrix &pixels, PixelPtrVector &sorted) const {
+        const int32_t pr = rows_ - 1, pc = cols_ - 1;
+        pixels.resize(pr, pc);                                                    // .cpp:58
+        for (int32_t i = 0; i < pr; ++i) {                                        // .cpp:59-63
+            pixels(i, 0).row = i;
+            pixels(i, pc - 1).row = i;
+            pixels(i, pc - 1).col = pc - 1;
+        }
+        for (int32_t i = 0; i < pc; ++i) {                                        // .cpp:64-68 (the (0, 1) index is the reference's)
+            pixels(0, 1).col = i;
+            pixels(pr - 1, i).col = i;
+            pixels(pr - 1, i).row = pr - 1;
+        }
+        for (int32_t col = 1; col < cols_ - 2; ++col) {                           // .cpp:71-89, same column-major walk
+            for (int32_t row = 1; row < rows_ - 2; ++row) {
+                auto &px = pixels(row, col);
+                const size_t at = size_t(row) * size_t(cols_) + size_t(col);
+                px.row = row;
+                px.col = col;
+                px.gradient_norm = norm_[at];
+                px.is_valid = norm_[at] > options_.kMinValidGradientNorm;
+                if (px.is_valid) px.line_level_angle = angle_[at];
+            }
+        }
+        const size_t before = sorted.size();
+        for (const int32_t s : seeds_) sorted.emplace_back(&pixels(s / cols_, s % cols_));   // .cpp:86, already in :92-94 order
+        if (before != 0) {
+            // the reference never clears sorted_pixels_ between calls and sorts the whole list again
+            std::stable_sort(sorted.begin(), sorted.end(), [](const auto *a, const auto *b) { return a->gradient_norm > b->gradient_norm; });
+        }
+    }
+
+    void set_device(int ordinal) { device_ = ordinal; }
+    const std::string &last_error() const { return last_error_; }
+
+private:
+    Options options_;
+    int32_t rows_ = 0, cols_ = 0;
+    std::vector<float> norm_, angle_;
+    std::vector<int32_t> seeds_;
+    int device_ = 0;
+    fd_context *ctx_ = nullptr;
+    std::string last_error_;
+};
+
+}  // namespace feature_detector
+
+#endif  // FD_B200_FEATURE_LINE_FIELD_H_

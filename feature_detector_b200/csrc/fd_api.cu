@@ -53,8 +53,9 @@ struct fd_context {
     bool have_desc = false;
 
     DevBuf mask_bits, mask_rowbase, mask_prefix, existing_xy, existing_counts;
-    int existing_capacity = 0;
+    int existing_capacity = 0, existing_frames = 0;
     bool have_existing = false;
+    MaskView mask_view = {};
 
     float *resp_map = nullptr;
     uint8_t *score_map = nullptr;
@@ -254,7 +255,6 @@ fd_status check_params(fd_context *ctx, const fd_detect_params *p) {
 fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_capacity) {
     FD_TRY(require_frames(ctx));
     FD_TRY(check_params(ctx, p));
-    if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not implemented in this build");
     const FrameView &fv = ctx->fv;
     const int64_t px = int64_t(fv.rows) * fv.cols;
     if (fv.rows > 65535 || fv.cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
@@ -268,6 +268,38 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     ctx->have_candidates = false;
     ctx->candidates_sorted = false;
     ctx->have_keypoints = false;
+
+    // pre-existing features: rasterise the bit mask for this call's min distance (feature_point_detector.cpp:12-16,90-98)
+    MaskView mask = {};
+    if (ctx->have_existing) {
+        if (ctx->existing_frames != fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "existing features were set for a different number of frames");
+        const int wpr = (fv.cols + 31) / 32 + 1;
+        const size_t words = size_t(fv.n_frames) * fv.rows * wpr;
+        FD_TRY(reserve(ctx, ctx->mask_bits, words * 4));
+        MaskArgs m = {};
+        m.rows = fv.rows;
+        m.cols = fv.cols;
+        m.n_frames = fv.n_frames;
+        m.min_distance = p->min_feature_distance;
+        m.xy = static_cast<const float *>(ctx->existing_xy.ptr);
+        m.counts = static_cast<const int32_t *>(ctx->existing_counts.ptr);
+        m.capacity = ctx->existing_capacity;
+        m.bits = static_cast<uint32_t *>(ctx->mask_bits.ptr);
+        m.words_per_row = wpr;
+        if (p->kind == FD_FAST) {
+            FD_TRY(reserve(ctx, ctx->mask_prefix, words * 4));
+            FD_TRY(reserve(ctx, ctx->mask_rowbase, size_t(fv.n_frames) * (fv.rows + 1) * 4));
+            m.word_prefix = static_cast<uint32_t *>(ctx->mask_prefix.ptr);
+            m.row_base = static_cast<uint32_t *>(ctx->mask_rowbase.ptr);
+        }
+        FD_CUDA(ctx, launch_mask(m, ctx->stream));
+        ++ctx->launches;
+        mask.bits = m.bits;
+        mask.word_prefix = m.word_prefix;
+        mask.row_base = m.row_base;
+        mask.words_per_row = wpr;
+    }
+    ctx->mask_view = mask;
 
     if (p->kind == FD_FAST) {
         if (ctx->score_map) FD_CUDA(ctx, cudaMemsetAsync(ctx->score_map, 0, size_t(fv.n_frames) * px, ctx->stream));
@@ -288,6 +320,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_map = ctx->score_map;
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
+            a.mask = mask;
             int grid;
             plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
@@ -311,6 +344,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.cand_capacity = cap;
             a.response_map = ctx->resp_map;
             a.n_strips = (fv.cols - 4 + CORNER_STRIP_OUT - 1) / CORNER_STRIP_OUT;
+            a.mask = mask;
             int grid;
             plan_bands(ctx, fv.rows - 4, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
@@ -356,6 +390,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     a.alive_scratch = static_cast<uint8_t *>(ctx->alive.ptr);
     a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
+    a.mask = ctx->mask_view;
     FD_CUDA(ctx, launch_select(a, ctx->stream));
     ++ctx->launches;
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
@@ -478,8 +513,19 @@ fd_status fd_set_existing_features(fd_context *ctx, const float *host_xy, const 
         ctx->have_existing = false;
         return FD_OK;
     }
-    (void)host_xy; (void)host_counts; (void)capacity;
-    return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not implemented in this build");
+    if (!host_xy || !host_counts || capacity <= 0 || n_frames < 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_set_existing_features: bad argument");
+    for (int f = 0; f < n_frames; ++f)
+        if (host_counts[f] < 0 || host_counts[f] > capacity) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "existing feature count exceeds capacity");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(reserve(ctx, ctx->existing_xy, size_t(n_frames) * capacity * 8));
+    FD_TRY(reserve(ctx, ctx->existing_counts, size_t(n_frames) * 4));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->existing_xy.ptr, host_xy, size_t(n_frames) * capacity * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->existing_counts.ptr, host_counts, size_t(n_frames) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's buffers may be pageable and reused right away
+    ctx->existing_capacity = capacity;
+    ctx->existing_frames = n_frames;
+    ctx->have_existing = true;
+    return FD_OK;
 }
 
 fd_status fd_set_dense_outputs(fd_context *ctx, float *dev_response_map, uint8_t *dev_fast_score_map) {

@@ -58,6 +58,14 @@ __device__ __forceinline__ uint32_t ld_word(const uint8_t *p) { return __ldg(rei
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Bits of mask word w (columns 32w .. 32w+31) that are FAST-interior columns [3, cols-4].
+__device__ __forceinline__ uint32_t fast_interior_bits(int w, int cols) {
+    const int lo = max(3 - 32 * w, 0), hi = min(cols - 4 - 32 * w, 31);
+    if (lo > 31 || hi < 0 || lo > hi) return 0u;
+    const uint32_t upto_hi = (hi == 31) ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u);
+    return upto_hi & ~((1u << lo) - 1u);
+}
+
 // Warp-aggregated append of up to `n_mine` keys per lane into a per-frame slot.  Returns false if the
 // slot overflowed (the counter still advances, so the host sees the true demand).
 __device__ __forceinline__ uint32_t warp_reserve(uint32_t *counter, uint32_t n_mine) {

@@ -90,7 +90,7 @@ __device__ __forceinline__ float response_of(float sxx, float syy, float sxy, co
     }
 }
 
-template <int KIND>
+template <int KIND, bool MASKED>
 __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerArgs p) {
     const FrameView &fv = p.fv;
     const int lane = lane_id();
@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
         uint32_t *counter = p.cand_counts + frame;
         uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
         float *resp_map = p.response_map ? p.response_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
+        // pre-existing features: the response is only evaluated where the mask is set (harris.cpp:94), 0 elsewhere
+        const uint32_t *mbits = MASKED ? p.mask.bits + int64_t(frame) * fv.rows * p.mask.words_per_row + (c0 >> 5) : nullptr;
 
         // Pixel row n arrives at step n.  Slots rotate with period 3: row q lives in slot q mod 3 (shifted
         // so that the unrolled phase index is a compile-time constant).
@@ -176,6 +178,13 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                     const int q = n - 2;
                     const bool q_valid = (q >= row_lo && q <= row_hi);
                     float rq[4];
+                    uint32_t mnib = 0xFu;  // mask bits of columns c0 .. c0+3 of row q
+                    if (MASKED) {
+                        if (q_valid && c0 < fv.cols) {
+                            const uint32_t *mp = mbits + int64_t(q) * p.mask.words_per_row;
+                            mnib = __funnelshift_r(__ldg(mp), __ldg(mp + 1), c0 & 31) & 0xFu;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int32_t ixx = hs[cur].xx[j] + hs[p2].xx[j] + hs[p1].xx[j];  // harris.cpp:81-88,108-116
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                         const float sxx = __fsub_rn(__int_as_float(ixx), kSumBasePos);
                         const float syy = __fsub_rn(__int_as_float(iyy), kSumBasePos);
                         const float sxy = __fsub_rn(__int_as_float(ixy), kSumBaseMid);
-                        rq[j] = (q_valid && col_valid[j]) ? response_of<KIND>(sxx, syy, sxy, p) : 0.0f;
+                        rq[j] = (q_valid && col_valid[j] && ((mnib >> j) & 1u)) ? response_of<KIND>(sxx, syy, sxy, p) : 0.0f;
                     }
                     if (resp_map != nullptr && q >= rb && q < re) {
 #pragma unroll
@@ -230,8 +239,14 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
 }  // namespace
 
 cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream) {
-    if (args.kind == 0) corner_kernel<0><<<grid, CORNER_THREADS, 0, stream>>>(args);
-    else corner_kernel<1><<<grid, CORNER_THREADS, 0, stream>>>(args);
+    const bool masked = args.mask.bits != nullptr;
+    if (args.kind == 0) {
+        if (masked) corner_kernel<0, true><<<grid, CORNER_THREADS, 0, stream>>>(args);
+        else corner_kernel<0, false><<<grid, CORNER_THREADS, 0, stream>>>(args);
+    } else {
+        if (masked) corner_kernel<1, true><<<grid, CORNER_THREADS, 0, stream>>>(args);
+        else corner_kernel<1, false><<<grid, CORNER_THREADS, 0, stream>>>(args);
+    }
     return cudaGetLastError();
 }
 

@@ -184,7 +184,7 @@ __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const 
     scores_packed = sp & pass;
 }
 
-template <bool PRECHECK, bool SCORE_MAP>
+template <bool PRECHECK, bool SCORE_MAP, bool MASKED>
 __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(const FastArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *lut = smem;                                               // 65536 B: run-length table
@@ -251,20 +251,38 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
         uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
         uint8_t *score_ptr = nullptr;
         if (SCORE_MAP) score_ptr = p.score_map + (int64_t(frame) * fv.rows + row_begin) * fv.cols + col0;
+        // Pre-existing features (MASKED): masked-out pixels are neither scored nor counted by the running offset
+        // (fast.cpp:88), so the pixel index k comes from the mask's prefix counts instead of the raster formula.
+        const int mwpr = p.mask.words_per_row;
+        const uint32_t *mbits = nullptr, *mprefix = nullptr, *mrow_base = nullptr;
+        uint32_t m_interior = 0u;
+        if (MASKED) {
+            mbits = p.mask.bits + int64_t(frame) * fv.rows * mwpr + (col0 >> 5);
+            mprefix = p.mask.word_prefix + int64_t(frame) * fv.rows * mwpr + (col0 >> 5);
+            mrow_base = p.mask.row_base + int64_t(frame) * (fv.rows + 1);
+            m_interior = fast_interior_bits(col0 >> 5, fv.cols);
+        }
+        // k of the first interior pixel of row r (r in [3, rows-3]; rows-3 gives the total)
+        auto row_k0 = [&](int r) -> uint32_t { return MASKED ? __ldg(mrow_base + r) : uint32_t(r - 3) * uint32_t(inner_cols); };
+        bool group_empty = false;
 
         for (int row = row_begin; row < row_end; ++row) {
             // The row loop is deliberately NOT unrolled: the seven window rows shift down by register moves instead of
             // by renaming, which keeps the whole kernel inside the instruction cache (an unrolled-by-7 body does not fit
             // and stalls on instruction fetch).
             if (((row - row_begin) % 7) == 0) {
-                const uint32_t k_first = uint32_t(row - 3) * uint32_t(inner_cols);
-                const uint32_t k_last = uint32_t(min(row + 6, row_end - 1) - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
-                while (s_last > 0 && p.kmin[s_last - 1] <= k_last) --s_last;
-                while (s_first > 0 && p.kmin[s_first - 1] <= k_first) --s_first;
-                while (k_first >= segs[seg + 1].k_start) ++seg;  // warp-uniform, monotonic over the band
+                const uint32_t k_first = row_k0(row);
+                const uint32_t k_end = row_k0(min(row + 7, row_end));  // one past the last pixel index of the group
+                group_empty = (k_end == k_first);                      // (only a mask can empty a group)
+                if (!group_empty) {
+                    const uint32_t k_last = k_end - 1u;
+                    while (s_last > 0 && p.kmin[s_last - 1] <= k_last) --s_last;
+                    while (s_first > 0 && p.kmin[s_first - 1] <= k_first) --s_first;
+                    while (k_first >= segs[seg + 1].k_start) ++seg;  // warp-uniform, monotonic over the band
+                }
             }
             // adding need_add to the packed scores sets bit 7 of every byte whose score >= s_last
-            const uint32_t need_add = (s_last > 16) ? 0u : (0x80u - uint32_t(s_last)) * 0x01010101u;
+            const uint32_t need_add = (s_last > 16 || group_empty) ? 0u : (0x80u - uint32_t(s_last)) * 0x01010101u;
             const int prune = SCORE_MAP ? 0 : (s_last >= 8 ? 2 : (s_last >= 4 ? 1 : 0));
 
             // the row that enters the window next step (row + 4)
@@ -296,11 +314,25 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
             // response = score + offset(k), k = index of the pixel among the masked-in interior pixels in raster
             // order (fast.cpp:85-93).  Only rows holding a pixel whose score can reach the threshold get here, and
             // only those pixels do the float work.  Candidates go to the warp's staging buffer.
-            const uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels with score >= s_last
+            uint32_t able = (sp + need_add) & col_ok & 0x80808080u;  // interior pixels with score >= s_last
+            uint32_t mword = 0u;
+            if (MASKED) {
+                if (able != 0u) {
+                    mword = __ldg(mbits + int64_t(row) * mwpr);
+                    const uint32_t nib = (mword >> (col0 & 31)) & 0xFu;               // mask bits of this lane's 4 pixels
+                    able &= ((nib * 0x00204081u) & 0x01010101u) * 0x80u;              // bit j -> bit 7 of byte j
+                }
+            }
             if (__any_sync(0xffffffffu, able != 0u)) {
                 const int r = row;
-                const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
-                const uint32_t k_lo = k_row + uint32_t(max(col0 - 3, 0));  // <= k of every interior pixel of this lane
+                uint32_t k_row, k_lo;  // k_lo <= k of every interior pixel of this lane
+                if (MASKED) {
+                    k_row = row_k0(r);
+                    k_lo = (able != 0u) ? k_row + __ldg(mprefix + int64_t(r) * mwpr) : k_row;
+                } else {
+                    k_row = uint32_t(r - 3) * uint32_t(inner_cols);
+                    k_lo = k_row + uint32_t(max(col0 - 3, 0));
+                }
                 int sg = seg;
                 if (able != 0u)
                     while (k_lo >= segs[sg + 1].k_start) ++sg;
@@ -310,7 +342,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
                 for (int j = 0; j < 4; ++j) {
                     resp[j] = 0.0f;
                     if ((able >> (8 * j + 7)) & 1u) {
-                        const uint32_t k = k_row + uint32_t(col0 + j - 3);
+                        const uint32_t k = MASKED ? k_lo + __popc(mword & m_interior & ((1u << ((col0 & 31) + j)) - 1u))
+                                                  : k_row + uint32_t(col0 + j - 3);
                         int sj = sg;
                         while (k >= segs[sj + 1].k_start) ++sj;
                         const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
@@ -363,19 +396,25 @@ size_t fast_smem_bytes(int n_seg) {
     return 65536 + FAST_MAX_SEGS * sizeof(OffsetSeg) + size_t(FAST_THREADS / 32) * FAST_STAGE_KEYS * 8;
 }
 
-template <bool PRECHECK, bool SCORE_MAP>
+template <bool PRECHECK, bool SCORE_MAP, bool MASKED>
 static cudaError_t launch_fast_t(const FastArgs &args, int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(fast_kernel<PRECHECK, SCORE_MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(fast_kernel<PRECHECK, SCORE_MAP, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    fast_kernel<PRECHECK, SCORE_MAP><<<grid, FAST_THREADS, smem, stream>>>(args);
+    fast_kernel<PRECHECK, SCORE_MAP, MASKED><<<grid, FAST_THREADS, smem, stream>>>(args);
     return cudaGetLastError();
+}
+
+template <bool PRECHECK, bool SCORE_MAP>
+static cudaError_t launch_fast_m(const FastArgs &args, int grid, size_t smem, cudaStream_t stream) {
+    return args.mask.bits != nullptr ? launch_fast_t<PRECHECK, SCORE_MAP, true>(args, grid, smem, stream)
+                                     : launch_fast_t<PRECHECK, SCORE_MAP, false>(args, grid, smem, stream);
 }
 
 cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes(args.n_seg);
     const bool sm = args.score_map != nullptr;
-    if (precheck) return sm ? launch_fast_t<true, true>(args, grid, smem, stream) : launch_fast_t<true, false>(args, grid, smem, stream);
-    return sm ? launch_fast_t<false, true>(args, grid, smem, stream) : launch_fast_t<false, false>(args, grid, smem, stream);
+    if (precheck) return sm ? launch_fast_m<true, true>(args, grid, smem, stream) : launch_fast_m<true, false>(args, grid, smem, stream);
+    return sm ? launch_fast_m<false, true>(args, grid, smem, stream) : launch_fast_m<false, false>(args, grid, smem, stream);
 }
 
 }  // namespace fdb

@@ -5,6 +5,26 @@
 
 namespace fdb {
 
+// ---- mask of pre-existing features (feature_point_detector.cpp:76-98), fd_mask.cu ----------------
+// One bit per pixel, words_per_row = ceil(cols / 32) + 1 words per row (the spare word lets a kernel read the
+// word pair that straddles any 4-pixel group without a bounds test).  bits == nullptr means "no mask".
+struct MaskView {
+    const uint32_t *bits;         // n_frames * rows * words_per_row
+    const uint32_t *word_prefix;  // FAST only: masked-in interior pixels of the row before each word
+    const uint32_t *row_base;     // FAST only: n_frames * (rows + 1); masked-in interior pixels in rows < r
+    int words_per_row;
+};
+struct MaskArgs {
+    int rows, cols, n_frames;
+    int min_distance;
+    const float *xy;              // n_frames slots of `capacity` (x, y) pairs
+    const int32_t *counts;
+    int capacity;
+    uint32_t *bits, *word_prefix, *row_base;  // word_prefix / row_base may be null (not FAST)
+    int words_per_row;
+};
+cudaError_t launch_mask(const MaskArgs &args, cudaStream_t stream);
+
 // ---- kernel 2: FAST --------------------------------------------------------------------------
 constexpr int FAST_THREADS = 256;
 constexpr int FAST_CTAS_PER_SM = 2;
@@ -32,6 +52,7 @@ struct FastArgs {
     int score_aligned;        // score_map rows can be written as aligned words
     int n_strips, n_bands, band_rows;
     int64_t n_items;
+    MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
 };
 size_t fast_smem_bytes(int n_seg);
 cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream);
@@ -52,6 +73,7 @@ struct CornerArgs {
     float *response_map;      // optional dense thresholded response map, may be null
     int n_strips, n_bands, band_rows;
     int64_t n_items;
+    MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
 };
 cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream);
 
@@ -80,6 +102,7 @@ struct SelectArgs {
     uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
+    MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
 };
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
 
@@ -114,8 +137,5 @@ cudaError_t launch_seed_sort(uint64_t *keys, const uint32_t *counts, int64_t slo
 // ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
 cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity, uint32_t *overflow_flag,
                                 cudaStream_t stream);
-
-// ---- mask from pre-existing features ------------------------------------------------------------
-// (feature_point_detector.cpp:76-98) -- filled in by fd_mask.cu
 
 }  // namespace fdb

@@ -160,7 +160,18 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
         min_hi[i] = 0xFFFFFFFFu;
         min_lo[i] = 0xFFFFFFFFu;
     }
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) alive[i] = 1;
+    if (p.mask.bits != nullptr) {
+        // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66).  Candidate generation
+        // already honours the mask; this only matters where a zero response can pass a negative threshold.
+        const uint32_t *mb = p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t xy = cand_key_xy(__ldg(keys + i));
+            const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
+            alive[i] = uint8_t((mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) alive[i] = 1;
+    }
     if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
 

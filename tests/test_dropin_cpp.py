@@ -1,0 +1,89 @@
+"""The C++ drop-in classes (feature_detector_b200/cpp) replaying the reference's demo sequences.
+
+fd_dropin_check runs test/test_feature_point_detector.cpp, test_feature_descriptor.cpp and the dense stage of
+test_feature_line_detector.cpp through the reference-named classes; its output is compared with the golden answers
+(regenerated from the reference build by tests/golden/make_golden.py).
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "feature_detector_b200", "cpp")
+EXE = os.path.join(CPP, "fd_dropin_check")
+
+
+@pytest.fixture(scope="module")
+def dropin_output(built, image_png, tmp_path_factory):
+    r = subprocess.run(["make", "-C", CPP], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    raw = tmp_path_factory.mktemp("dropin") / "image_752x480.u8"
+    raw.write_bytes(image_png.tobytes())
+    r = subprocess.run([EXE, str(raw), "480", "752"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads(r.stdout)
+
+
+def test_dropin_headers_keep_the_reference_surface():
+    """Names a caller of the reference compiles against."""
+    hdr = open(os.path.join(CPP, "feature_point_detector.h")).read()
+    for name in ("namespace feature_detector", "class FeaturePointDetector", "class FeaturePointHarrisDetector", "class FeaturePointShiTomasDetector",
+                 "class FeaturePointFastDetector", "bool DetectGoodFeatures(const GrayImage &image, const uint32_t needed_feature_num, std::vector<Vec2> &features)",
+                 "void SparsifyFeatures(", "kMinFeatureDistance = 15", "kGridFilterRowDivideNumber = 12", "kMinValidResponse = 0.1f", "Options &options()",
+                 "candidates()", "mask()", '"Harris"', '"Shi-Tomas"', '"Fast"', "kN = 12", "kMinPixelDiffValue = 15"):
+        assert name in hdr, name
+    for inc in ("feature_point_harris_detector.h", "feature_point_shi_tomas_detector.h", "feature_point_fast_detector.h", "descriptor.h", "descriptor_brief.h"):
+        assert os.path.exists(os.path.join(CPP, inc)), inc
+    brief = open(os.path.join(CPP, "descriptor_brief.h")).read()
+    for name in ("using BriefType = std::vector<bool>", "class BriefDescriptor", "kLength = 256", "kHalfPatchSize = 8"):
+        assert name in brief, name
+
+
+def test_dropin_has_no_cpu_path(dropin_output):
+    """Without a CUDA device every GPU-backed call returns false; with one, this test is vacuous."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    out = dropin_output
+    assert out["fast_demo"]["ok"] is False and out["harris_demo"]["ok"] is False and out["brief_harris10"]["ok"] is False
+    assert out["lsd_field"]["ok"] is False and out["fast_demo"]["n_feat"] == 0
+    assert out["null_image_returns"] is False
+
+
+@pytest.mark.gpu
+def test_dropin_replays_reference_demos(dropin_output, kat):
+    out = dropin_output
+    gold = {(c["detector"], c["thr"]): c for c in kat["cases"] if c["frame"] == "image" and "thr" in c}
+    for label, key, name in (("fast_demo", ("fast", 10.0), "Fast"), ("harris_demo", ("harris", 30.0), "Harris"), ("shi_demo", ("shi", 40.0), "Shi-Tomas"),
+                             ("fast9_demo", ("fast9", 10.0), "Fast"), ("harris_default_reused", ("harris", 0.1), "Harris")):
+        o, g = out[label], gold[key]
+        assert o["ok"] is True and o["name"] == name
+        assert o["n_cand"] == g["n_cand"], label
+        assert o["n_feat"] == g["n_feat_raster_ties"] and o["feat_hash"] == g["feat_hash_raster_ties"], label
+        assert (o["mask_rows"], o["mask_cols"]) == (480, 752)
+    # SURVEY.md 8c first features
+    assert out["fast_demo"]["first"] == [45, 471] and out["harris_demo"]["first"] == [74, 3] and out["shi_demo"]["first"] == [639, 63]
+    pre = out["harris_preseeded81"]
+    g = [c for c in kat["cases"] if c["detector"] == "harris_preseeded81"][0]
+    assert pre["n_pre"] == 81 and pre["n_feat"] == g["n_feat"] == 200 and pre["n_cand"] == g["n_cand"] and pre["feat_hash"] == g["feat_hash"]
+    assert pre["first"] == [520, 201]
+    # mask(): FAST demo found 84 < 200 features, so every feature cleared its clipped 41x41 square
+    assert 0 < out["fast_demo"]["mask_zeros"] <= 84 * 41 * 41
+    assert out["null_image_returns"] is False
+
+    b = out["brief_harris10"]
+    g = [c for c in kat["cases"] if c["frame"] == "image" and c["detector"] == "brief" and c["set"] == "harris10"][0]
+    assert b["ok"] is True and b["n"] == 10 and b["length"] == 128
+    assert (b["ones"], b["all_zero"], b["hash"]) == (g["ones"], g["all_zero"], g["hash"])
+    assert b["float_sum"] == 2.0 * g["ones"] - 10 * 128          # bits -> +1 / -1 (descriptor.h:51-54)
+    assert b["empty_returns"] is False                            # descriptor.h:29
+
+    l = out["lsd_field"]
+    g = [c for c in kat["cases"] if c["frame"] == "image" and c["detector"] == "lsd"][0]
+    assert l["ok"] is True and (l["rows"], l["cols"]) == (479, 751)
+    assert l["n_valid"] == l["n_sorted"] == g["n_valid"] and l["norm_hash"] == g["norm_hash"] and l["sorted_norm_hash"] == g["sorted_norm_hash"]
+    assert abs(l["norm_sum"] - g["norm_sum"]) < 1e-3 and abs(l["angle_sum"] - g["angle_sum"]) < 1e-5 * g["n_valid"]
+    assert l["descending"] is True and l["positions_ok"] is True

@@ -272,3 +272,89 @@ def test_bound_device_frames_with_pitch(ctx, checker, torch_cuda):
         for f in range(3):
             o = checker.detect(FAST, batch[f], 10.0, 20, 200, fast_n=9)
             assert np.array_equal(np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1), o["features"])
+
+
+# ---- pre-existing features: the in/out `features` argument (feature_point_detector.cpp:12-16, 90-98) -------------
+def _pre_sets(w, h, rng):
+    grid = np.array([[15.0 * i, 15.0 * j] for i in range(1, 10) for j in range(1, 10)], np.float32)  # the demo's 81 seeds
+    rand = np.stack([rng.uniform(-30, w + 30, 40), rng.uniform(-30, h + 30, 40)], 1).astype(np.float32)  # fractional, some outside
+    return {"grid81": grid, "random_fractional": rand, "corner_cases": np.array([[0, 0], [w - 1, h - 1], [w + 5, 3], [-0.5, -0.5], [3.9, 3.9]], np.float32)}
+
+
+@pytest.mark.parametrize("shape_idx", [(752, 480, 0), (333, 217, 5), (130, 70, 9)])
+@pytest.mark.parametrize("case", [("fast", 10.0, 20, 200, 12), ("fast", 10.0, 20, 200, 9), ("fast", 0.1, 15, 300, 12), ("fast", 0.5, 6, 500, 9),
+                                  ("harris", 30.0, 20, 200, 12), ("harris", 0.1, 15, 1000, 12), ("shi", 40.0, 20, 300, 12)])
+def test_detect_with_existing_features_vs_checker(ctx, checker, shape_idx, case):
+    from feature_detector_b200.synth import synth
+    w, h, idx = shape_idx
+    name, thr, d, n, fast_n = case
+    im = synth(w, h, idx)
+    rng = np.random.default_rng(idx)
+    try:
+        for label, pre in _pre_sets(w, h, rng).items():
+            o = checker.detect(KIND[name], im, thr, d, n, fast_n=fast_n, pre=pre)
+            ctx.upload(im)
+            ctx.set_existing_features([pre])
+            ctx.detect(fd.DetectParams(KIND[name], thr, d, n, fast_n=fast_n))
+            kp, cnt = ctx.keypoints(max(n, 1))
+            cand = ctx.candidates(0)
+            new = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32)
+            _assert_same_candidates(cand, o)
+            assert np.array_equal(o["features"][:len(pre)], pre), label       # the reference keeps the seeds in front
+            ref_new = o["features"][len(pre):]
+            if not np.array_equal(new, ref_new):
+                assert name != "fast", label                                   # FAST has no ties
+                assert same_up_to_ties(o["cand_resp"], o["cand_xy"], cand["response"], np.stack([cand["x"], cand["y"]], 1)), label
+                assert len(new) == len(ref_new), label
+    finally:
+        ctx.set_existing_features([])
+
+
+def test_existing_features_count_toward_needed(ctx, checker, image_png):
+    """needed <= len(existing): the reference still pushes exactly one new feature (push, then test; :67-68)."""
+    pre = np.array([[15.0 * i, 15.0 * j] for i in range(1, 10) for j in range(1, 10)], np.float32)
+    try:
+        for needed in (0, 50, 81, 82, 100):
+            o = checker.detect(HARRIS, image_png, 30.0, 20, needed, pre=pre)
+            ctx.upload(image_png)
+            ctx.set_existing_features([pre])
+            ctx.detect(fd.DetectParams(fd.HARRIS, 30.0, 20, needed))
+            kp, cnt = ctx.keypoints(max(needed, 1))
+            new = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32)
+            assert np.array_equal(new, o["features"][len(pre):]), needed
+    finally:
+        ctx.set_existing_features([])
+
+
+def test_golden_preseeded_harris(ctx, image_png, kat):
+    """Harris thr 30 + 81 pre-seeded (15i, 15j): 12 194 candidates, 119 new features, first new (520, 201)."""
+    pre = np.array([[15.0 * i, 15.0 * j] for i in range(1, 10) for j in range(1, 10)], np.float32)
+    try:
+        ctx.upload(image_png)
+        ctx.set_existing_features([pre])
+        ctx.detect(fd.DetectParams(fd.HARRIS, 30.0, 20, 200))
+        kp, cnt = ctx.keypoints(200)
+        assert int(ctx.candidate_counts()[0]) == 12194
+        assert cnt[0] == 119 and (kp["x"][0, 0], kp["y"][0, 0]) == (520.0, 201.0)
+        full = np.concatenate([pre, np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1)]).astype("<i4")
+        assert fnv(full) == "85bd4f625b5448b3"
+    finally:
+        ctx.set_existing_features([])
+
+
+def test_existing_features_per_frame_in_a_batch(ctx, checker):
+    from feature_detector_b200.synth import synth
+    ims = np.stack([synth(320, 200, i) for i in range(4)])
+    rng = np.random.default_rng(7)
+    pres = [np.stack([rng.uniform(0, 320, k), rng.uniform(0, 200, k)], 1).astype(np.float32) for k in (0, 5, 60, 1)]
+    try:
+        ctx.upload(ims)
+        ctx.set_existing_features(pres)
+        ctx.detect(fd.DetectParams(fd.FAST, 0.3, 10, 150, fast_n=9))
+        kp, cnt = ctx.keypoints(150)
+        for f in range(4):
+            o = checker.detect(FAST, ims[f], 0.3, 10, 150, fast_n=9, pre=pres[f])
+            new = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
+            assert np.array_equal(new, o["features"][len(pres[f]):]), f
+    finally:
+        ctx.set_existing_features([])
