@@ -3,10 +3,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
+
+#include <cuda.h>
 
 #include "../../include/fd_b200.h"
 #include "fd_kernels.cuh"
@@ -59,6 +62,11 @@ struct fd_context {
 
     float *resp_map = nullptr;
     uint8_t *score_map = nullptr;
+
+    // TMA view of the bound frames for the sparse FAST kernel (rebuilt when the binding changes)
+    CUtensorMap frame_map;
+    bool frame_map_valid = false, frame_map_failed = false;
+    bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted;
     float *lsd_norm_p = nullptr, *lsd_angle_p = nullptr;
@@ -221,6 +229,38 @@ fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
     return FD_OK;
 }
 
+// 3-D TMA map (cols x rows x frames, u8) with a 160 x 16 x 1 box for the sparse FAST kernel.  Needs 16-byte aligned base,
+// pitch and frame stride; returns false (and the dense kernel is used) when the layout or the driver does not allow it.
+bool ensure_frame_map(fd_context *ctx) {
+    if (ctx->frame_map_valid) return true;
+    if (ctx->frame_map_failed) return false;
+    const FrameView &fv = ctx->fv;
+    ctx->frame_map_failed = true;
+    if (reinterpret_cast<uintptr_t>(fv.data) % 16 != 0 || fv.pitch % 16 != 0 || fv.frame_stride % 16 != 0) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {cuuint64_t(fv.cols), cuuint64_t(fv.rows), cuuint64_t(fv.n_frames)};
+    const cuuint64_t strides[2] = {cuuint64_t(fv.pitch), cuuint64_t(fv.frame_stride)};
+    const cuuint32_t box[3] = {160u, 16u, 1u};  // box starts are 16-byte aligned: strip * 128 - 16
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(&ctx->frame_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(fv.data), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    ctx->frame_map_failed = false;
+    ctx->frame_map_valid = true;
+    return true;
+}
+
 // Split the interior rows into bands so that every resident warp gets several work items.
 void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_frames, int warps_per_cta, int ctas_per_sm, int min_band,
                 int band_multiple, int &band_rows, int &n_bands, int64_t &n_items, int &grid) {
@@ -321,9 +361,23 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
             a.mask = mask;
+            // Sparse form: when the threshold leaves s_min >= 4 (>= 1 with the pre-check: a failed pre-check scores 0) at
+            // every pixel of the frame, most words are ruled out by the compass test and only the rest are scored.
+            const bool precheck = p->fast_n >= 12;
+            int shift = 0;
+            while ((2 << shift) <= p->fast_min_pixel_diff + 1) ++shift;   // 2^shift = largest power of two <= diff + 1
+            a.absdiff_shift = shift;
+            a.absdiff_mask = ((0xFFu << shift) & 0xFFu) * 0x01010101u;
+            const bool prunable = precheck ? (a.kmin[0] == 0xFFFFFFFFu && shift >= 1) : (a.kmin[3] == 0xFFFFFFFFu);
+            const bool sparse = prunable && !ctx->force_dense_fast && mask.bits == nullptr && ctx->score_map == nullptr && ensure_frame_map(ctx);
             int grid;
-            plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
-            FD_CUDA(ctx, launch_fast(a, p->fast_n >= 12, grid, ctx->stream));
+            if (sparse) {
+                plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                FD_CUDA(ctx, launch_fast_sparse(a, &ctx->frame_map, precheck, grid, ctx->stream));
+            } else {
+                plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                FD_CUDA(ctx, launch_fast(a, precheck, grid, ctx->stream));
+            }
             ++ctx->launches;
         }
     } else {
@@ -427,6 +481,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
         return FD_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     *out_ctx = ctx;
@@ -481,6 +536,7 @@ fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows
     }
     ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, pitch, stride, n_frames, int(pitch / 4)};
     ctx->frames_bound = true;
+    ctx->frame_map_valid = ctx->frame_map_failed = false;
     ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
     return FD_OK;
 }
@@ -503,6 +559,7 @@ fd_status fd_bind_device_frames(fd_context *ctx, const uint8_t *dev_frames, int 
         ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, np, ns, n_frames, int(np / 4)};
     }
     ctx->frames_bound = true;
+    ctx->frame_map_valid = ctx->frame_map_failed = false;
     ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
     return FD_OK;
 }

@@ -53,9 +53,16 @@ struct FastArgs {
     int n_strips, n_bands, band_rows;
     int64_t n_items;
     MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
+    uint32_t absdiff_mask;    // sparse kernel: per byte, the bits at or above 2^absdiff_shift
+    int absdiff_shift;        // 2^absdiff_shift = largest power of two <= diff + 1
 };
 size_t fast_smem_bytes(int n_seg);
 cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream);
+// Sparse form (fd_fast_sparse.cu): needs a 3-D TMA map of the frames (a CUtensorMap, 128 bytes, passed opaquely),
+// no mask, no score map, and a threshold that leaves s_min >= 4 (>= 1 with the pre-check) over the whole frame.
+constexpr int FAST_SPARSE_THREADS = 512;
+size_t fast_sparse_smem_bytes();
+cudaError_t launch_fast_sparse(const FastArgs &args, const void *tensor_map, bool precheck, int grid, cudaStream_t stream);
 
 // ---- kernel 1: Harris / Shi-Tomasi -------------------------------------------------------------
 constexpr int CORNER_THREADS = 256;

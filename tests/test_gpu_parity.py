@@ -358,3 +358,64 @@ def test_existing_features_per_frame_in_a_batch(ctx, checker):
             assert np.array_equal(new, o["features"][len(pres[f]):]), f
     finally:
         ctx.set_existing_features([])
+
+
+# ---- sparse FAST kernel (fd_fast_sparse.cu): same candidates as the dense kernel / the reference, bit for bit ----------
+@pytest.fixture(scope="module")
+def dense_ctx():
+    """A context pinned to the dense FAST kernel (FD_B200_FAST_DENSE is read when the context is created)."""
+    import os
+    os.environ["FD_B200_FAST_DENSE"] = "1"
+    try:
+        c = fd.Context(0)
+    finally:
+        del os.environ["FD_B200_FAST_DENSE"]
+    yield c
+    c.close()
+
+
+def _cand_table(ctx, frame=0):
+    c = ctx.candidates(frame)
+    t = np.zeros((len(c), 3), np.uint32)
+    t[:, 0] = c["response"].view(np.uint32)
+    t[:, 1] = c["x"]
+    t[:, 2] = c["y"]
+    return t
+
+
+@pytest.mark.parametrize("shape_idx", [(752, 480, 3), (333, 217, 5), (130, 70, 9), (1001, 37, 3), (64, 48, 1), (1280, 720, 4), (2048, 131, 6)])
+@pytest.mark.parametrize("fast_n", [9, 12])
+def test_fast_sparse_thresholds_vs_checker(ctx, checker, shape_idx, fast_n):
+    """Thresholds that put s_min anywhere in 1..17 (the sparse kernel's ANY / ADJ / PRE word tests and the switch rows)."""
+    from feature_detector_b200.synth import synth
+    w, h, idx = shape_idx
+    im = synth(w, h, idx)
+    ctx.upload(im)
+    for thr in (4.05, 5.0, 7.0, 7.99, 8.0, 9.5, 10.0, 12.0, 15.9, 16.5, 1.0, 0.9):
+        o = checker.detect(FAST, im, thr, 20, 100, fast_n=fast_n)
+        ctx.detect(fd.DetectParams(fd.FAST, thr, 20, 100, fast_n=fast_n))
+        _assert_same_candidates(ctx.candidates(0), o)
+        kp, cnt = ctx.keypoints(100)
+        assert np.array_equal(np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1), o["features"]), (thr, fast_n)
+
+
+@pytest.mark.parametrize("fast_n", [9, 12])
+def test_fast_sparse_equals_dense_other_diffs_and_batches(ctx, dense_ctx, fast_n):
+    from feature_detector_b200.synth import synth
+    rng = np.random.default_rng(5)
+    batches = [np.stack([synth(320, 200, i) for i in range(24)]),
+               rng.integers(0, 256, (5, 97, 259), dtype=np.uint8),                      # pure noise: nearly every word survives
+               np.stack([synth(752, 480, 40 + i) for i in range(3)])]
+    for frames in batches:
+        ctx.upload(frames)
+        dense_ctx.upload(frames)
+        for diff, thr in ((1, 9.0), (7, 6.0), (15, 10.0), (16, 10.0), (31, 5.0), (40, 8.5), (100, 4.5), (255, 4.5), (0, 12.0)):
+            prm = fd.DetectParams(fd.FAST, thr, 12, 50, fast_n=fast_n, fast_min_pixel_diff=diff)
+            ctx.detect(prm)
+            dense_ctx.detect(prm)
+            assert np.array_equal(ctx.candidate_counts(), dense_ctx.candidate_counts()), (diff, thr)
+            for f in range(len(frames)):
+                assert np.array_equal(_cand_table(ctx, f), _cand_table(dense_ctx, f)), (diff, thr, f)
+            kp_a, cnt_a = ctx.keypoints(50)
+            kp_b, cnt_b = dense_ctx.keypoints(50)
+            assert np.array_equal(cnt_a, cnt_b) and np.array_equal(kp_a, kp_b)
