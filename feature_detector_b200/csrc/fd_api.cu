@@ -251,7 +251,7 @@ bool ensure_frame_map(fd_context *ctx) {
     }
     const cuuint64_t dims[3] = {cuuint64_t(fv.cols), cuuint64_t(fv.rows), cuuint64_t(fv.n_frames)};
     const cuuint64_t strides[2] = {cuuint64_t(fv.pitch), cuuint64_t(fv.frame_stride)};
-    const cuuint32_t box[3] = {160u, 16u, 1u};  // box starts are 16-byte aligned: strip * 128 - 16
+    const cuuint32_t box[3] = {160u, cuuint32_t(FAST_SPARSE_GROUP_ROWS), 1u};  // box starts are 16-byte aligned: strip * 128 - 16
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = encode(&ctx->frame_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(fv.data), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -373,6 +373,11 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             int grid;
             if (sparse) {
                 plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                if (a.band_rows > 2032) {  // the kernel's queue entries keep the band-local row in 11 bits
+                    a.band_rows = 2032;
+                    a.n_bands = (fv.rows - 6 + a.band_rows - 1) / a.band_rows;
+                    a.n_items = int64_t(fv.n_frames) * a.n_strips * a.n_bands;
+                }
                 FD_CUDA(ctx, launch_fast_sparse(a, &ctx->frame_map, precheck, grid, ctx->stream));
             } else {
                 plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);

@@ -21,12 +21,14 @@
 //   B (sparse, exact): surviving words are queued per warp; every 32 of them are scored by the full half2 ring test of
 //     fd_fast_ring.cuh, one word (4 pixels) per lane, and emit candidates exactly as the dense kernel does.
 //
-// Data movement: each warp owns a 128-pixel column strip and streams down a band of rows through a private 64-row ring
-// in shared memory that TMA fills 16 rows at a time (cp.async.bulk.tensor, 3-D map cols x rows x frames, box 160 x 16 x 1,
+// Data movement: each warp owns a 128-pixel column strip and streams down a band of rows through a private 32-row ring
+// in shared memory that TMA fills 8 rows at a time (cp.async.bulk.tensor, 3-D map cols x rows x frames, box 160 x 8 x 1,
 // out-of-frame bytes zero-filled by the hardware), one group ahead of the row being tested.  Phase A reads five
 // conflict-free words per row; phase B gathers its 21 words per lane from the same ring.  HBM traffic is the frame,
 // once, plus the candidate keys.
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "fd_fast_ring.cuh"
 
@@ -37,22 +39,23 @@ namespace {
 using namespace fastring;
 
 constexpr int SP_WARPS = FAST_SPARSE_THREADS / 32;
-constexpr int SP_RING_ROWS = 64;                    // rows resident per warp (power of two)
-constexpr int SP_GROUP_ROWS = 16;                   // rows per TMA box
+constexpr int SP_RING_ROWS = 4 * FAST_SPARSE_GROUP_ROWS;  // rows resident per warp (power of two)
+constexpr int SP_GROUP_ROWS = FAST_SPARSE_GROUP_ROWS;  // rows per TMA box
 constexpr int SP_GROUPS = SP_RING_ROWS / SP_GROUP_ROWS;
 constexpr int SP_ROW_WORDS = 40;                    // 160-byte box rows: 16-byte halo, 32 strip words, 16-byte halo (TMA box starts must be 16-byte aligned)
 constexpr int SP_W0 = 3;                            // ring word that holds the 4 pixels left of lane 0's own word
-constexpr int SP_QUEUE = 64;                        // survivor queue entries per warp (power of two, >= 32 + 31)
+constexpr int SP_QUEUE = 512;                       // survivor queue entries per warp (power of two, >= 31 + 32 * SP_GROUP_ROWS)
 constexpr int SP_STAGE = 192;                       // candidate staging keys per warp (a batch adds at most 128)
 constexpr uint32_t SP_GROUP_BYTES = SP_GROUP_ROWS * SP_ROW_WORDS * 4;
 
 struct WarpSmem {
     uint32_t ring[SP_RING_ROWS * SP_ROW_WORDS];     // must stay first: TMA destinations need 128-byte alignment
     uint64_t stage[SP_STAGE];
-    uint32_t queue[SP_QUEUE];
+    uint16_t queue[SP_QUEUE];                       // (local centre row << 5) | lane; bands are at most 2040 rows
     uint64_t bar[SP_GROUPS];
     uint32_t pad[24];                               // keeps sizeof(WarpSmem) a multiple of 128
 };
+static_assert(SP_GROUP_ROWS >= 6 && SP_QUEUE >= 32 + 32 * SP_GROUP_ROWS, "ring / queue geometry");
 static_assert(sizeof(WarpSmem) % 128 == 0, "per-warp shared block must keep the rings 128-byte aligned");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -76,7 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// 3-D tiled TMA load: box (160 bytes, 16 rows, 1 frame) at (x, y, frame) into shared memory, completing on `bar`.
+// 3-D tiled TMA load: box (160 bytes, 8 rows, 1 frame) at (x, y, frame) into shared memory, completing on `bar`.
 __device__ __forceinline__ void tma_load_rows(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
@@ -138,7 +141,6 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
         };
 
         issue_group(0);
-        if (n_groups > 1) issue_group(1);
 
         const int col0 = strip * 128 + 4 * lane;
         uint32_t col_ok = 0u;  // 0xFF per interior column [3, cols-4] of this lane
@@ -236,56 +238,88 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
             }
         };
 
-        // ---- phase A over the band, 16 rows per TMA group ----
-        // Centre lc needs ring rows lc-3 .. lc+3, i.e. groups up to (lc + 3) / 16.  When lc + 3 enters group g, group
-        // g + 1 is requested; it overwrites group g - 3, so every queued word must have lc - 3 >= 16 (g - 2).
-        wait_group(0);
+        // ---- phase A over the band, one TMA group (8 rows) per step ----
+        // Step g tests the 8 centre rows lc = 8 g - 3 + i, whose ring neighbourhood lc - 3 .. lc + 3 lies in ring groups
+        // g - 1 and g; group g + 1 is requested at the start of the step and overwrites group g - 3, which queued words
+        // of steps <= g - 2 would still need, so those are drained first.  Inside a step every shared-memory address is
+        // a group base plus a compile-time offset, and each lane collects its 8 survivor flags in one register.
         const int lc_end = n_rows + 3;
-        for (int lc = 3; lc < lc_end; ++lc) {
-            if (((lc + 3) & (SP_GROUP_ROWS - 1)) == 0) {
-                const int g = (lc + 3) / SP_GROUP_ROWS;
-                if (g + 1 < n_groups) {
-                    while (qh < qn) {   // warp-uniform
-                        const int oldest = int(ws.queue[qh & (SP_QUEUE - 1)] >> 5);
-                        if (oldest - 3 >= SP_GROUP_ROWS * (g - 2)) break;
-                        drain_batch();
-                    }
-                    issue_group(g + 1);
+        for (int g = 0;; ++g) {
+            // The one place phase B runs (a single copy of its code keeps the kernel inside the instruction cache):
+            // full batches, anything step g's TMA request would strand, and at the end of the band whatever is left.
+            while (qh < qn) {   // warp-uniform
+                if (qn - qh < 32u && g < n_groups) {
+                    const int oldest_step = (int(ws.queue[qh & (SP_QUEUE - 1)] >> 5) + 3) / SP_GROUP_ROWS;
+                    if (oldest_step >= g - 1 || g + 1 >= n_groups) break;
                 }
-                wait_group(g);
+                drain_batch();
             }
-            // s_min of this row's last pixel decides how strong the word test may be
-            const uint32_t *rc = &ws.ring[(lc & (SP_RING_ROWS - 1)) * SP_ROW_WORDS + SP_W0 + lane];
-            const uint32_t wl = rc[0], wc = rc[1], wr = rc[2];
-            const uint32_t up = ws.ring[((lc - 3) & (SP_RING_ROWS - 1)) * SP_ROW_WORDS + SP_W0 + 1 + lane];
-            const uint32_t dn = ws.ring[((lc + 3) & (SP_RING_ROWS - 1)) * SP_ROW_WORDS + SP_W0 + 1 + lane];
-            const uint32_t a4 = __vabsdiffu4(__funnelshift_r(wc, wr, 24), wc);   // ring 4: (row, col + 3)
-            const uint32_t a12 = __vabsdiffu4(__funnelshift_r(wl, wc, 8), wc);   // ring 12: (row, col - 3)
-            const uint32_t a8 = __vabsdiffu4(dn, wc);                            // ring 8: (row + 3, col)
-            bool surv;
-            if (PRECHECK) {
-                // right, bottom and left all differ by more than diff in the same pixel: (x >> s) + 0x7f sets bit 7 per byte
-                const uint32_t f4 = ((a4 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
-                const uint32_t f8 = ((a8 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
-                const uint32_t f12 = ((a12 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
-                surv = (f4 & f8 & f12 & 0x80808080u) != 0u;
-            } else {
-                const uint32_t a0 = __vabsdiffu4(up, wc);                        // ring 0: (row - 3, col)
-                const int r = row_begin - 3 + lc;
-                const uint32_t k_row_last = uint32_t(r - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
-                const bool adj = p.kmin[7] > k_row_last;                         // score 7 cannot pass in this row: s_min >= 8
-                if (adj) surv = (((a0 | a8) & hm) != 0u) && (((a4 | a12) & hm) != 0u);
-                else surv = ((a0 | a4 | a8 | a12) & hm) != 0u;
+            if (g == n_groups) break;
+            if (g + 1 < n_groups) issue_group(g + 1);
+            wait_group(g);
+            const uint32_t *cur = &ws.ring[(g & (SP_GROUPS - 1)) * SP_GROUP_ROWS * SP_ROW_WORDS + SP_W0 + lane];
+            const uint32_t *prev = &ws.ring[((g - 1) & (SP_GROUPS - 1)) * SP_GROUP_ROWS * SP_ROW_WORDS + SP_W0 + lane];
+            const int lc0 = SP_GROUP_ROWS * g - 3;
+            // ADJ is allowed when score 7 cannot pass anywhere in the step's rows (kmin is non-increasing in the score)
+            bool adj = false;
+            if (!PRECHECK) {
+                const int r_last = row_begin - 3 + min(lc0 + SP_GROUP_ROWS - 1, lc_end - 1);
+                adj = p.kmin[7] > uint32_t(r_last - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
             }
-            surv = surv && (col_ok != 0u);
-            const uint32_t b = __ballot_sync(0xffffffffu, surv);
-            if (b != 0u) {
-                if (surv) ws.queue[(qn + __popc(b & ((1u << lane) - 1u))) & (SP_QUEUE - 1)] = (uint32_t(lc) << 5) | uint32_t(lane);
-                qn += __popc(b);
-                if (qn - qh >= 32u) drain_batch();
+            uint32_t bits = 0u;   // bit i: this lane's word of centre row lc0 + i survives
+            auto test_rows = [&](auto mode_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;   // 0 ANY, 1 ADJ, 2 PRE
+#pragma unroll
+                for (int i = 0; i < SP_GROUP_ROWS; ++i) {
+                    const uint32_t *rc = (i >= 3) ? cur + (i - 3) * SP_ROW_WORDS : prev + (SP_GROUP_ROWS - 3 + i) * SP_ROW_WORDS;
+                    const uint32_t *ru = (i >= 6) ? cur + (i - 6) * SP_ROW_WORDS : prev + (SP_GROUP_ROWS - 6 + i) * SP_ROW_WORDS;
+                    const uint32_t wl = rc[0], wc = rc[1], wr = rc[2];
+                    const uint32_t a4 = __vabsdiffu4(__funnelshift_r(wc, wr, 24), wc);          // ring 4: (row, col + 3)
+                    const uint32_t a12 = __vabsdiffu4(__funnelshift_r(wl, wc, 8), wc);          // ring 12: (row, col - 3)
+                    const uint32_t a8 = __vabsdiffu4(cur[(i) * SP_ROW_WORDS + 1], wc);          // ring 8: (row + 3, col)
+                    bool surv;
+                    if (MODE == 2) {
+                        // right, bottom and left all differ by more than diff in the same pixel: (x >> s) + 0x7f sets bit 7 per byte
+                        const uint32_t f4 = ((a4 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
+                        const uint32_t f8 = ((a8 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
+                        const uint32_t f12 = ((a12 & hm) >> p.absdiff_shift) + 0x7F7F7F7Fu;
+                        surv = (f4 & f8 & f12 & 0x80808080u) != 0u;
+                    } else {
+                        const uint32_t a0 = __vabsdiffu4(ru[1], wc);                            // ring 0: (row - 3, col)
+                        if (MODE == 1) surv = (((a0 | a8) & hm) != 0u) && (((a4 | a12) & hm) != 0u);
+                        else surv = ((a0 | a4 | a8 | a12) & hm) != 0u;
+                    }
+                    if (surv) bits |= 1u << i;
+                }
+            };
+            if (PRECHECK) test_rows(std::integral_constant<int, 2>());
+            else if (adj) test_rows(std::integral_constant<int, 1>());
+            else test_rows(std::integral_constant<int, 0>());
+            // rows outside the band (the halo rows of the first and last step) and lanes outside the interior drop out
+            {
+                const int lo = max(3 - lc0, 0), hi = min(lc_end - lc0, SP_GROUP_ROWS);   // live centre rows: i in [lo, hi)
+                const uint32_t live = (hi > lo) ? (((1u << (hi - lo)) - 1u) << lo) : 0u;
+                bits &= (col_ok != 0u) ? live : 0u;
+            }
+            // bulk append of the step's survivors: exclusive prefix of the per-lane counts, then each lane writes its rows
+            if (__any_sync(0xffffffffu, bits != 0u)) {
+                const uint32_t cnt = __popc(bits);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                uint32_t pos = qn + incl - cnt;
+                qn += __shfl_sync(0xffffffffu, incl, 31);
+                while (bits != 0u) {
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    ws.queue[pos & (SP_QUEUE - 1)] = uint16_t((uint32_t(lc0 + i) << 5) | uint32_t(lane));
+                    ++pos;
+                }
             }
         }
-        while (qh < qn) drain_batch();
         if (n_staged != 0u) flush_stage();
         __syncwarp();
     }

@@ -60,7 +60,8 @@ size_t fast_smem_bytes(int n_seg);
 cudaError_t launch_fast(const FastArgs &args, bool precheck, int grid, cudaStream_t stream);
 // Sparse form (fd_fast_sparse.cu): needs a 3-D TMA map of the frames (a CUtensorMap, 128 bytes, passed opaquely),
 // no mask, no score map, and a threshold that leaves s_min >= 4 (>= 1 with the pre-check) over the whole frame.
-constexpr int FAST_SPARSE_THREADS = 512;
+constexpr int FAST_SPARSE_THREADS = 768;
+constexpr int FAST_SPARSE_GROUP_ROWS = 8;   // rows per TMA box (the host builds the tensor map with this box height)
 size_t fast_sparse_smem_bytes();
 cudaError_t launch_fast_sparse(const FastArgs &args, const void *tensor_map, bool precheck, int grid, cudaStream_t stream);
 
