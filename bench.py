@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--fast-n", dest="fast_n", type=int, default=9, help="9 = full segment test on every pixel (configs[1] 'FAST-9'); 12 = reference default")
+    ap.add_argument("--chunk", type=int, default=128, help="frames per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (kN=12, Harris, Shi-Tomasi, LSD)")
     args = ap.parse_args()
 
@@ -278,19 +279,24 @@ def main():
             pass
 
     # ---- e2e: pinned host frames in, keypoints + descriptors back on the host, every step -------------
-    kp_host = np.zeros((n, NEEDED), fd.KEYPOINT_DTYPE)
+    # The public host-batch call (feature_detector_b200.pipeline.HostPipeline.run): chunks of frames alternate between
+    # two contexts so that the PCIe copies of one chunk overlap the kernels of the other.
+    from feature_detector_b200.pipeline import HostPipeline
+    pinned_kp = torch.zeros((n, NEEDED, 16), dtype=torch.uint8).pin_memory()
+    pinned_cnt = torch.zeros((n,), dtype=torch.int32).pin_memory()
+    pinned_desc = torch.zeros((n, NEEDED, 32), dtype=torch.uint8).pin_memory()
+    kp_host = pinned_kp.numpy().view(fd.KEYPOINT_DTYPE).reshape(n, NEEDED)
+    cnt_host = pinned_cnt.numpy()
+    desc_host = pinned_desc.numpy()
     h2d = n * px
     d2h = n * NEEDED * 16 + n * 4 + n * NEEDED * 32
+    pipe = HostPipeline(local_rank, chunk_frames=args.chunk)
 
     def e2e_step():
-        ctx.upload_ptr(host.data_ptr(), H, W, n)
-        ctx.detect(det, CAND_CAPACITY)
-        ctx.describe_selected(brief)
-        ctx.keypoints(NEEDED)
-        ctx.descriptors(NEEDED)
+        pipe.run(host.data_ptr(), H, W, n, det, brief, kp_host, cnt_host, desc_host, CAND_CAPACITY)
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -299,6 +305,8 @@ def main():
     barrier()
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * px * e2e_steps / e2e_sec / 1e6
+    e2e_match = bool(np.array_equal(cnt_host, kp_counts))  # the pipelined result equals the device-resident run
+    pipe.close()
 
     extras = {}
     if not args.no_extras:
@@ -339,7 +347,9 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_sec / e2e_steps * 1e3, 3), "steps": e2e_steps,
-                    "path": "fd_upload_frames (pinned host) -> fd_detect -> fd_describe_selected -> fd_download_keypoints + fd_download_descriptors"},
+                    "path": f"HostPipeline.run: chunks of {args.chunk} frames on two contexts; per chunk fd_upload_frames (pinned host) -> fd_detect -> "
+                            "fd_describe_selected -> fd_download_keypoints + fd_download_descriptors (pinned host)",
+                    "matches_device_resident_run": e2e_match},
             "gpu_launches": int(launches), "clocks": clocks,
             "mean_keypoints_per_frame": float(kp_counts.mean()), "mean_candidates_per_frame": float(cand_counts.mean()),
             "extras": extras,

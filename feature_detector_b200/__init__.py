@@ -230,6 +230,11 @@ class Context:
         self._ck(self._lib.fd_download_keypoints(self._h, kp.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.POINTER(C.c_int32)), kp_capacity))
         return kp, counts
 
+    def keypoints_into(self, kp: np.ndarray, counts: np.ndarray):
+        """Like keypoints(), into caller-owned arrays (e.g. views of pinned memory): kp (n_frames, capacity) KEYPOINT_DTYPE, counts int32."""
+        assert kp.dtype == KEYPOINT_DTYPE and kp.flags.c_contiguous and kp.shape[0] == self.n_frames and counts.dtype == np.int32
+        self._ck(self._lib.fd_download_keypoints(self._h, kp.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.POINTER(C.c_int32)), kp.shape[1]))
+
     def keypoint_counts(self):
         counts = np.zeros(self.n_frames, np.int32)
         self._ck(self._lib.fd_download_keypoints(self._h, None, counts.ctypes.data_as(C.POINTER(C.c_int32)), 0))
@@ -273,6 +278,11 @@ class Context:
         d = np.zeros((self.n_frames, kp_capacity, 32), np.uint8)
         self._ck(self._lib.fd_download_descriptors(self._h, d.ctypes.data_as(C.c_void_p), kp_capacity))
         return d
+
+    def descriptors_into(self, desc: np.ndarray):
+        """Like descriptors(), into a caller-owned (n_frames, capacity, 32) uint8 array."""
+        assert desc.dtype == np.uint8 and desc.flags.c_contiguous and desc.shape[0] == self.n_frames and desc.shape[2] == 32
+        self._ck(self._lib.fd_download_descriptors(self._h, desc.ctypes.data_as(C.c_void_p), desc.shape[1]))
 
     # -- LSD -----------------------------------------------------------------------------------------
     def lsd_field(self, params: LsdParams, dev_norm: int = 0, dev_angle: int = 0, dev_sorted: int = 0, dev_n_valid: int = 0):

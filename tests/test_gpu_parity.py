@@ -419,3 +419,27 @@ def test_fast_sparse_equals_dense_other_diffs_and_batches(ctx, dense_ctx, fast_n
             kp_a, cnt_a = ctx.keypoints(50)
             kp_b, cnt_b = dense_ctx.keypoints(50)
             assert np.array_equal(cnt_a, cnt_b) and np.array_equal(kp_a, kp_b)
+
+
+def test_host_pipeline_equals_single_call(ctx, torch_cuda):
+    """Chunked, double-buffered host batches (pipeline.HostPipeline) give what one fd_detect over the batch gives."""
+    from feature_detector_b200.pipeline import HostPipeline
+    from feature_detector_b200.synth import synth
+    torch = torch_cuda
+    frames = np.stack([synth(320, 200, 100 + i) for i in range(21)])
+    host = torch.from_numpy(frames).pin_memory()
+    det, brief = fd.DetectParams(fd.FAST, 10.0, 12, 60, fast_n=9), fd.BriefParams(256, 8)
+    ctx.upload(frames)
+    ctx.detect(det)
+    ctx.describe_selected(brief)
+    kp_ref, cnt_ref = ctx.keypoints(60)
+    desc_ref = ctx.descriptors(60)
+    kp = np.zeros((21, 60), fd.KEYPOINT_DTYPE)
+    cnt = np.zeros(21, np.int32)
+    desc = np.zeros((21, 60, 32), np.uint8)
+    with HostPipeline(0, chunk_frames=4) as pipe:   # 6 chunks, the last one ragged
+        for _ in range(2):                            # second pass reuses the contexts' buffers
+            pipe.run(host.data_ptr(), 200, 320, 21, det, brief, kp, cnt, desc)
+            assert np.array_equal(cnt, cnt_ref)
+            for f in range(21):
+                assert np.array_equal(kp[f, :cnt[f]], kp_ref[f, :cnt[f]]) and np.array_equal(desc[f, :cnt[f]], desc_ref[f, :cnt[f]])
