@@ -97,6 +97,10 @@ def load_library():
         "fd_download_candidates": (C.c_int, [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64)]),
         "fd_candidate_counts": (C.c_int, [vp, i32p]),
         "fd_device_keypoints": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int)]),
+        "fd_set_tile": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "fd_device_candidates": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]),
+        "fd_export_candidates": (C.c_int, [vp, vp, C.c_int64, C.POINTER(C.c_int64)]),
+        "fd_select_candidates": (C.c_int, [vp, C.POINTER(DetectParams), vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_int]),
         "fd_sparsify": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint8, C.c_uint8, u8p]),
         "fd_describe_selected": (C.c_int, [vp, C.POINTER(BriefParams)]),
         "fd_describe_points": (C.c_int, [vp, C.POINTER(BriefParams), f32p, i32p, C.c_int, C.c_int]),
@@ -251,6 +255,27 @@ class Context:
         out = np.zeros(n.value, CANDIDATE_DTYPE)
         self._ck(self._lib.fd_download_candidates(self._h, frame, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return out
+
+    # -- row tiles of one large frame ------------------------------------------------------------------
+    def set_tile(self, row_offset: int, own_first_row: int, own_row_count: int, full_rows: int):
+        """The bound frames are rows [row_offset, row_offset + rows) of an image full_rows tall; full_rows <= 0 clears."""
+        self._ck(self._lib.fd_set_tile(self._h, row_offset, own_first_row, own_row_count, full_rows))
+
+    def device_candidates(self):
+        """(dev_keys ptr, dev_counts ptr, capacity) of the last fd_compute_candidates."""
+        keys, cnt, cap = C.c_void_p(), C.c_void_p(), C.c_uint32(0)
+        self._ck(self._lib.fd_device_candidates(self._h, C.byref(keys), C.byref(cnt), C.byref(cap)))
+        return keys.value, cnt.value, cap.value
+
+    def export_candidates(self, dev_dst: int, dst_capacity: int):
+        """Pack all frames' candidate keys into device memory at dev_dst (int64 / uint64 elements); returns per-frame counts."""
+        counts = np.zeros(self.n_frames, np.int64)
+        self._ck(self._lib.fd_export_candidates(self._h, C.c_void_p(dev_dst), dst_capacity, counts.ctypes.data_as(C.POINTER(C.c_int64))))
+        return counts
+
+    def select_candidates(self, params: DetectParams, dev_keys: int, dev_counts: int, capacity: int, rows: int, cols: int, n_frames: int = 1):
+        self._ck(self._lib.fd_select_candidates(self._h, C.byref(params), C.c_void_p(dev_keys), C.c_void_p(dev_counts), capacity, rows, cols, n_frames))
+        self.n_frames = n_frames
 
     def device_keypoints(self):
         kp, cnt, cap = C.c_void_p(), C.c_void_p(), C.c_int(0)

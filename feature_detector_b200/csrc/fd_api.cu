@@ -46,6 +46,7 @@ struct fd_context {
     DevBuf kp, kp_counts;
     int kp_capacity = 0;
     bool have_keypoints = false;
+    int select_frames = 0;     // frames the last selection covered (the bound frames, or external candidates)
 
     DevBuf user_kp, user_counts;
     int user_capacity = 0;
@@ -62,6 +63,9 @@ struct fd_context {
 
     float *resp_map = nullptr;
     uint8_t *score_map = nullptr;
+
+    bool tiled = false;        // fd_set_tile: the bound frames are a row tile of a taller image
+    TileView tile = {};
 
     // TMA view of the bound frames for the sparse FAST kernel (rebuilt when the binding changes)
     CUtensorMap frame_map;
@@ -297,7 +301,14 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     FD_TRY(check_params(ctx, p));
     const FrameView &fv = ctx->fv;
     const int64_t px = int64_t(fv.rows) * fv.cols;
-    if (fv.rows > 65535 || fv.cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
+    TileView tile = {0, 0, fv.rows, fv.rows};
+    if (ctx->tiled) {
+        tile = ctx->tile;
+        if (tile.own_lo < 0 || tile.own_hi > fv.rows || tile.own_lo > tile.own_hi || tile.row_offset < 0 || tile.row_offset + fv.rows > tile.full_rows)
+            return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_set_tile: the tile does not fit the bound frames");
+        if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing feature masks are not supported on row tiles");
+    }
+    if (tile.full_rows > 65535 || fv.cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
     const uint32_t cap = cand_capacity > 0 ? uint32_t(std::min<int64_t>(cand_capacity, px)) : uint32_t(px);
     ctx->cand_capacity = cap;
     FD_TRY(reserve(ctx, ctx->keys, size_t(fv.n_frames) * cap * 8));
@@ -344,7 +355,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     if (p->kind == FD_FAST) {
         if (ctx->score_map) FD_CUDA(ctx, cudaMemsetAsync(ctx->score_map, 0, size_t(fv.n_frames) * px, ctx->stream));
         if (fv.rows >= 7 && fv.cols >= 7) {
-            const uint32_t interior = uint32_t(fv.rows - 6) * uint32_t(fv.cols - 6);
+            const uint32_t interior = uint32_t(tile.full_rows - 6) * uint32_t(fv.cols - 6);
             FD_TRY(ensure_fast_tables(ctx, interior));
             FastArgs a = {};
             a.fv = fv;
@@ -361,6 +372,10 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.score_aligned = (fv.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(ctx->score_map) % 4 == 0);
             a.n_strips = (fv.cols + 127) / 128;
             a.mask = mask;
+            a.tile = tile;
+            a.proc_lo = std::max(3, tile.own_lo);
+            a.proc_hi = std::max(a.proc_lo, std::min(std::min(fv.rows - 3, tile.own_hi), tile.full_rows - 3 - tile.row_offset));
+            const int proc_rows = a.proc_hi - a.proc_lo;
             // Sparse form: when the threshold leaves s_min >= 4 (>= 1 with the pre-check: a failed pre-check scores 0) at
             // every pixel of the frame, most words are ruled out by the compass test and only the rest are scored.
             const bool precheck = p->fast_n >= 12;
@@ -369,18 +384,18 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.absdiff_shift = shift;
             a.absdiff_mask = ((0xFFu << shift) & 0xFFu) * 0x01010101u;
             const bool prunable = precheck ? (a.kmin[0] == 0xFFFFFFFFu && shift >= 1) : (a.kmin[3] == 0xFFFFFFFFu);
-            const bool sparse = prunable && !ctx->force_dense_fast && mask.bits == nullptr && ctx->score_map == nullptr && ensure_frame_map(ctx);
+            const bool sparse = prunable && proc_rows > 0 && !ctx->force_dense_fast && mask.bits == nullptr && ctx->score_map == nullptr && ensure_frame_map(ctx);
             int grid;
             if (sparse) {
-                plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);
                 if (a.band_rows > 2032) {  // the kernel's queue entries keep the band-local row in 11 bits
                     a.band_rows = 2032;
-                    a.n_bands = (fv.rows - 6 + a.band_rows - 1) / a.band_rows;
+                    a.n_bands = (proc_rows + a.band_rows - 1) / a.band_rows;
                     a.n_items = int64_t(fv.n_frames) * a.n_strips * a.n_bands;
                 }
                 FD_CUDA(ctx, launch_fast_sparse(a, &ctx->frame_map, precheck, grid, ctx->stream));
             } else {
-                plan_bands(ctx, fv.rows - 6, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
                 FD_CUDA(ctx, launch_fast(a, precheck, grid, ctx->stream));
             }
             ++ctx->launches;
@@ -404,8 +419,14 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.response_map = ctx->resp_map;
             a.n_strips = (fv.cols - 4 + CORNER_STRIP_OUT - 1) / CORNER_STRIP_OUT;
             a.mask = mask;
+            a.tile = tile;
+            // a response exists where the 5x5 neighbourhood is inside the FULL frame (harris.cpp:90-92) and inside this buffer
+            a.resp_lo = std::max(2, 2 - tile.row_offset);
+            a.resp_hi = std::min(fv.rows - 3, tile.full_rows - 3 - tile.row_offset);
+            a.cand_lo = std::max(a.resp_lo, tile.own_lo);
+            a.cand_hi = std::max(a.cand_lo, std::min(a.resp_hi + 1, tile.own_hi));
             int grid;
-            plan_bands(ctx, fv.rows - 4, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
+            plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
             FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
             ++ctx->launches;
         }
@@ -414,8 +435,11 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     return FD_OK;
 }
 
-fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
-    const FrameView &fv = ctx->fv;
+// Greedy selection over candidate keys of n_frames frames of rows x cols pixels (the context's own candidates, or keys
+// gathered from the row tiles of one frame).
+fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int cols, int n_frames, uint64_t *keys, const uint32_t *counts,
+                     uint32_t capacity) {
+    struct { int rows, cols, n_frames; } fv = {rows, cols, n_frames};
     const int kp_cap = int(std::max<uint32_t>(1u, std::min<uint32_t>(p->needed_feature_num, 1u << 20)));
     ctx->kp_capacity = kp_cap;
     FD_TRY(reserve(ctx, ctx->kp, size_t(fv.n_frames) * kp_cap * sizeof(float4)));
@@ -424,9 +448,9 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     a.rows = fv.rows;
     a.cols = fv.cols;
     a.n_frames = fv.n_frames;
-    a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
-    a.cand_counts = static_cast<const uint32_t *>(ctx->counts.ptr);
-    a.cand_capacity = ctx->cand_capacity;
+    a.cand_keys = keys;
+    a.cand_counts = counts;
+    a.cand_capacity = capacity;
     a.min_distance = p->min_feature_distance;
     a.needed = p->needed_feature_num;
     a.existing_counts = ctx->have_existing ? static_cast<const int32_t *>(ctx->existing_counts.ptr) : nullptr;
@@ -444,7 +468,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
     a.kept_capacity = a.cells_x * a.cells_y;
-    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * ctx->cand_capacity));
+    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
     a.alive_scratch = static_cast<uint8_t *>(ctx->alive.ptr);
     a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
@@ -454,6 +478,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p) {
     ++ctx->launches;
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
+    ctx->select_frames = fv.n_frames;
     return FD_OK;
 }
 
@@ -607,7 +632,69 @@ fd_status fd_detect(fd_context *ctx, const fd_detect_params *params, int cand_ca
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
     FD_CUDA(ctx, cudaSetDevice(ctx->device));
     FD_TRY(run_candidates(ctx, params, cand_capacity));
-    return run_select(ctx, params);
+    if (ctx->tiled) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_detect on a row tile: gather the tiles' candidates and call fd_select_candidates");
+    return run_select(ctx, params, ctx->fv.rows, ctx->fv.cols, ctx->fv.n_frames, static_cast<uint64_t *>(ctx->keys.ptr),
+                      static_cast<const uint32_t *>(ctx->counts.ptr), ctx->cand_capacity);
+}
+
+fd_status fd_set_tile(fd_context *ctx, int row_offset, int own_first_row, int own_row_count, int full_rows) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (full_rows <= 0) {
+        ctx->tiled = false;
+        return FD_OK;
+    }
+    if (row_offset < 0 || own_first_row < 0 || own_row_count < 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_set_tile: negative argument");
+    ctx->tile = TileView{row_offset, own_first_row, own_first_row + own_row_count, full_rows};
+    ctx->tiled = true;
+    return FD_OK;
+}
+
+fd_status fd_device_candidates(fd_context *ctx, const uint64_t **dev_keys, const uint32_t **dev_counts, uint32_t *capacity) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
+    if (dev_keys) *dev_keys = static_cast<const uint64_t *>(ctx->keys.ptr);
+    if (dev_counts) *dev_counts = static_cast<const uint32_t *>(ctx->counts.ptr);
+    if (capacity) *capacity = ctx->cand_capacity;
+    return FD_OK;
+}
+
+fd_status fd_export_candidates(fd_context *ctx, uint64_t *dev_dst, int64_t dst_capacity, int64_t *host_counts) {
+    if (!ctx || !dev_dst || !host_counts) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(check_overflow(ctx));
+    const int nf = ctx->fv.n_frames;
+    std::vector<uint32_t> counts(static_cast<size_t>(nf));
+    FD_CUDA(ctx, cudaMemcpyAsync(counts.data(), ctx->counts.ptr, size_t(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t total = 0;
+    for (int f = 0; f < nf; ++f) {
+        host_counts[f] = counts[f];
+        total += counts[f];
+    }
+    if (total > dst_capacity) return fail(ctx, FD_ERR_CAPACITY, "fd_export_candidates: destination too small");
+    int64_t at = 0;
+    for (int f = 0; f < nf; ++f) {
+        if (counts[f] == 0) continue;
+        FD_CUDA(ctx, cudaMemcpyAsync(dev_dst + at, static_cast<const uint64_t *>(ctx->keys.ptr) + int64_t(f) * ctx->cand_capacity, size_t(counts[f]) * 8,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        at += counts[f];
+    }
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, uint64_t *dev_keys, const uint32_t *dev_counts, uint32_t capacity,
+                               int rows, int cols, int n_frames) {
+    if (!ctx || !dev_keys || !dev_counts || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_select_candidates: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(check_params(ctx, params));
+    if (rows > 65535 || cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
+    FD_TRY(reserve(ctx, ctx->flags, 16));
+    if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing features are not supported with external candidates");
+    ctx->mask_view = MaskView{};
+    ctx->select_frames = n_frames;
+    return run_select(ctx, params, rows, cols, n_frames, dev_keys, dev_counts, capacity);
 }
 
 fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts) {
@@ -647,7 +734,7 @@ fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *
     if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
     if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
     FD_TRY(check_overflow(ctx));
-    const int nf = ctx->fv.n_frames;
+    const int nf = ctx->select_frames;
     FD_CUDA(ctx, cudaMemcpyAsync(host_counts, ctx->kp_counts.ptr, size_t(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_kp != nullptr) {
         static_assert(sizeof(fd_keypoint) == sizeof(float4), "fd_keypoint layout");

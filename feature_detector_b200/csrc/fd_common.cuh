@@ -20,6 +20,14 @@ struct FrameView {
     int words_per_row;     // readable aligned words per row = pitch / 4
 };
 
+// ---- row tiling of one large frame -------------------------------------------------
+// The bound buffer holds rows [row_offset, row_offset + fv.rows) of an image that is full_rows tall.  Candidates are
+// produced only for the local rows [own_lo, own_hi) (the rest is halo) and carry ABSOLUTE row numbers; FAST's running
+// offset is indexed by the absolute pixel position, so tiles are seam-free.  Untiled: {0, 0, rows, rows}.
+struct TileView {
+    int row_offset, own_lo, own_hi, full_rows;
+};
+
 // ---- candidate keys ------------------------------------------------------------------------------
 // One candidate = one 64-bit key: high word = bitwise complement of the order-preserving integer image
 // of the float response, low word = (row << 16) | col.  Sorting keys ASCENDING therefore yields response

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
     const int warps_per_block = blockDim.x >> 5;
     const int64_t total_warps = int64_t(gridDim.x) * warps_per_block;
     const int64_t gwarp = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
-    const int row_lo = 2, row_hi = fv.rows - 3;  // valid response rows (bound = 2, harris.cpp:90-92)
+    const int row_lo = p.resp_lo, row_hi = p.resp_hi;  // rows with a defined response (bound = 2, harris.cpp:90-92)
     const int col_lo = 2, col_hi = fv.cols - 3;
 
     for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);
         const int frame = int(t / p.n_bands);
-        const int rb = row_lo + band * p.band_rows;
-        const int re = min(rb + p.band_rows, row_hi + 1);
+        const int rb = p.cand_lo + band * p.band_rows;
+        const int re = min(rb + p.band_rows, p.cand_hi);
         if (rb >= re) continue;
 
         const int x0 = 1 + CORNER_STRIP_OUT * strip;  // first computed column of the strip
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 if ((mine >> j) & 1u) {
-                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[p2][j], uint32_t(m), uint32_t(c0 + j));
+                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[p2][j], uint32_t(m + p.tile.row_offset), uint32_t(c0 + j));
                                     ++pos;
                                 }
                             }

@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);
         const int frame = int(t / p.n_bands);
-        const int row_begin = 3 + band * p.band_rows;
-        const int row_end = min(row_begin + p.band_rows, fv.rows - 3);
+        const int row_begin = p.proc_lo + band * p.band_rows;
+        const int row_end = min(row_begin + p.band_rows, p.proc_hi);
         if (row_begin >= row_end) continue;
 
         // Rows are read as three aligned words per lane through three running pointers.  Addresses are clamped
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
             m_interior = fast_interior_bits(col0 >> 5, fv.cols);
         }
         // k of the first interior pixel of row r (r in [3, rows-3]; rows-3 gives the total)
-        auto row_k0 = [&](int r) -> uint32_t { return MASKED ? __ldg(mrow_base + r) : uint32_t(r - 3) * uint32_t(inner_cols); };
+        auto row_k0 = [&](int r) -> uint32_t { return MASKED ? __ldg(mrow_base + r) : uint32_t(r + p.tile.row_offset - 3) * uint32_t(inner_cols); };
         bool group_empty = false;
 
         for (int row = row_begin; row < row_end; ++row) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
                     k_row = row_k0(r);
                     k_lo = (able != 0u) ? k_row + __ldg(mprefix + int64_t(r) * mwpr) : k_row;
                 } else {
-                    k_row = uint32_t(r - 3) * uint32_t(inner_cols);
+                    k_row = uint32_t(r + p.tile.row_offset - 3) * uint32_t(inner_cols);
                     k_lo = k_row + uint32_t(max(col0 - 3, 0));
                 }
                 int sg = seg;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t m = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
-                    if ((mine >> j) & 1u) stage[base + __popc(m & ((1u << lane) - 1u))] = make_cand_key(resp[j], uint32_t(r), uint32_t(col0 + j));
+                    if ((mine >> j) & 1u) stage[base + __popc(m & ((1u << lane) - 1u))] = make_cand_key(resp[j], uint32_t(r + p.tile.row_offset), uint32_t(col0 + j));
                     base += __popc(m);
                 }
                 n_staged = base;

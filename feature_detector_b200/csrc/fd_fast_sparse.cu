@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);
         const int frame = int(t / p.n_bands);
-        const int row_begin = 3 + band * p.band_rows;
-        const int row_end = min(row_begin + p.band_rows, fv.rows - 3);
+        const int row_begin = p.proc_lo + band * p.band_rows;
+        const int row_end = min(row_begin + p.band_rows, p.proc_hi);
+        const int abs0 = p.tile.row_offset;   // absolute row of local row 0 (row tiles of a larger frame)
         if (row_begin >= row_end) continue;
         const int n_rows = row_end - row_begin;
         // local row index lr <-> image row (row_begin - 3 + lr); centre rows are lr = 3 .. n_rows + 2
@@ -151,13 +152,13 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
         // smallest score that can pass anywhere in this band: at its last pixel (kmin is non-increasing in s)
         int s_band = 17;
         {
-            const uint32_t k_last = uint32_t(row_end - 1 - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
+            const uint32_t k_last = uint32_t(row_end - 1 + abs0 - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
             while (s_band > 0 && p.kmin[s_band - 1] <= k_last) --s_band;
         }
         const uint32_t need_add = (s_band > 16) ? 0u : (0x80u - uint32_t(s_band)) * 0x01010101u;
         int seg_band = 0;
         {
-            const uint32_t k_first = uint32_t(row_begin - 3) * uint32_t(inner_cols);
+            const uint32_t k_first = uint32_t(row_begin + abs0 - 3) * uint32_t(inner_cols);
             while (k_first >= segs[seg_band + 1].k_start) ++seg_band;
         }
 
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
             sp &= ok;
             const uint32_t able = (sp + need_add) & ok & 0x80808080u;  // score >= s_band: may pass somewhere in the band
             if (__any_sync(0xffffffffu, able != 0u)) {
-                const int r = row_begin - 3 + lc;
+                const int r = row_begin - 3 + lc + abs0;   // absolute row
                 const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
                 int sg = seg_band;
                 if (able != 0u) {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
             // ADJ is allowed when score 7 cannot pass anywhere in the step's rows (kmin is non-increasing in the score)
             bool adj = false;
             if (!PRECHECK) {
-                const int r_last = row_begin - 3 + min(lc0 + SP_GROUP_ROWS - 1, lc_end - 1);
+                const int r_last = row_begin - 3 + abs0 + min(lc0 + SP_GROUP_ROWS - 1, lc_end - 1);
                 adj = p.kmin[7] > uint32_t(r_last - 3) * uint32_t(inner_cols) + uint32_t(inner_cols - 1);
             }
             uint32_t bits = 0u;   // bit i: this lane's word of centre row lc0 + i survives

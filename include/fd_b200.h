@@ -139,6 +139,25 @@ fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_
 fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts);
 fd_status fd_device_keypoints(fd_context *ctx, const fd_keypoint **dev_kp, const int32_t **dev_counts, int *kp_capacity);
 
+/* ---- one large frame, row-tiled across GPUs -----------------------------------------
+ * fd_set_tile declares the bound frames to be rows [row_offset, row_offset + rows) of an image full_rows tall, of which
+ * the local rows [own_first_row, own_first_row + own_row_count) are this tile's own and the rest is halo (3 rows each side
+ * cover Harris / Shi-Tomasi / FAST).  fd_compute_candidates then emits candidates for the own rows only, with ABSOLUTE row
+ * numbers, and FAST's running offset (fast.cpp:85-93) is indexed by the absolute pixel position, so tiles are seam-free.
+ * full_rows <= 0 clears the tile.  The candidate keys of all tiles are gathered by the caller (NCCL / peer copies; device
+ * pointers from fd_device_candidates) and handed to fd_select_candidates on one GPU: the greedy selection of
+ * feature_point_detector.cpp:54-74 is global per frame.  A key is 64 bits: high word = ~ordered(response) (ascending key
+ * = descending response), low word = (row << 16) | col. */
+fd_status fd_set_tile(fd_context *ctx, int row_offset, int own_first_row, int own_row_count, int full_rows);
+fd_status fd_device_candidates(fd_context *ctx, const uint64_t **dev_keys, const uint32_t **dev_counts, uint32_t *capacity);
+/* Pack the candidate keys of all bound frames back to back into caller-owned device memory (device-to-device);
+ * host_counts[f] receives each frame's count.  Synchronises. */
+fd_status fd_export_candidates(fd_context *ctx, uint64_t *dev_dst, int64_t dst_capacity, int64_t *host_counts);
+/* Selection over caller-supplied candidate keys: n_frames slots of `capacity` keys (dev_counts[f] valid) for frames of
+ * rows x cols pixels.  dev_keys is scratch-free but must be writable device memory.  Results: fd_download_keypoints. */
+fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, uint64_t *dev_keys, const uint32_t *dev_counts, uint32_t capacity,
+                               int rows, int cols, int n_frames);
+
 /* FeaturePointDetector::SparsifyFeatures (feature_point_detector.cpp:27-52): first-come grid filter over an
  * existing feature list.  Pure host-side integer logic over at most a few thousand points; kept in the
  * library so the drop-in class has one implementation.  status is in/out (n entries). */
