@@ -464,13 +464,13 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
     a.cells_in_smem = cell_bytes * 3 <= 24 * 1024;
     if (!a.cells_in_smem) {
-        FD_TRY(reserve(ctx, ctx->cells, cell_bytes * 3 * fv.n_frames));
+        FD_TRY(reserve(ctx, ctx->cells, (cell_bytes * 3 + 4) * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
     a.kept_capacity = a.cells_x * a.cells_y;
-    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity));
+    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 8));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
-    a.alive_scratch = static_cast<uint8_t *>(ctx->alive.ptr);
+    a.live_scratch = static_cast<uint32_t *>(ctx->alive.ptr);
     a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;

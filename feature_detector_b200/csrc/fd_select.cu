@@ -110,7 +110,7 @@ __device__ __forceinline__ bool near_kept(const uint32_t *cells, int cells_x, in
 }
 
 // Best (smallest) key posted to the 3x3 cells around (cx, cy), the centre cell excluded.
-__device__ __forceinline__ uint64_t neighbour_min(const uint32_t *min_hi, const uint32_t *min_lo, int cells_x, int cells_y, int cx, int cy) {
+__device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin, int cells_x, int cells_y, int cx, int cy) {
     uint64_t best = kDeadKey;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
@@ -119,12 +119,21 @@ __device__ __forceinline__ uint64_t neighbour_min(const uint32_t *min_hi, const 
             if (dx == 0 && dy == 0) continue;
             const int xx = cx + dx, yy = cy + dy;
             if (xx < 0 || yy < 0 || xx >= cells_x || yy >= cells_y) continue;
-            const int c = yy * cells_x + xx;
-            const uint64_t k = (uint64_t(min_hi[c]) << 32) | min_lo[c];
-            best = min(best, k);
+            best = min(best, uint64_t(cmin[yy * cells_x + xx]));
         }
     }
     return best;
+}
+
+// Unordered append of this thread's surviving candidate index to a list (warp-aggregated counter bump).
+__device__ __forceinline__ void list_push(bool keep, uint32_t value, uint32_t *list, uint32_t *counter) {
+    const uint32_t m = __ballot_sync(__activemask(), keep);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if (lane_id() == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(__activemask(), base, leader);
+    if (keep) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
 }
 
 __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs p) {
@@ -132,47 +141,40 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
     const int frame = blockIdx.x;
     const int d = p.min_distance;
     const int n_cells = p.cells_x * p.cells_y;
-    // shared (or, for very fine grids, global) per-cell state
-    uint32_t *cells, *min_hi, *min_lo;
+    // per-cell state, shared (or, for very fine grids, global): best live key posted this round, and the kept point
+    unsigned long long *cmin;
+    uint32_t *cells;
     if (p.cells_in_smem) {
-        cells = reinterpret_cast<uint32_t *>(smem);
-        min_hi = cells + n_cells;
-        min_lo = min_hi + n_cells;
+        cmin = reinterpret_cast<unsigned long long *>(smem);
+        cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     } else {
-        cells = p.cell_scratch + int64_t(frame) * n_cells * 3;
-        min_hi = cells + n_cells;
-        min_lo = min_hi + n_cells;
+        cmin = reinterpret_cast<unsigned long long *>(p.cell_scratch + int64_t(frame) * ((n_cells * 3 + 1) & ~1));  // keeps 8-byte alignment
+        cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     }
-    __shared__ uint32_t s_kept, s_alive;
+    __shared__ uint32_t s_kept, s_count[2];
     __shared__ uint64_t s_sort[SELECT_SORT_SMEM];
 
     const uint32_t count = p.cand_counts[frame];
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
-    uint8_t *alive = p.alive_scratch + int64_t(frame) * p.cand_capacity;
+    // two index lists (live candidates of the current / next round), ping-pong
+    uint32_t *list_a = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
+    uint32_t *list_b = list_a + p.cand_capacity;
     uint64_t *kept = p.kept_keys + int64_t(frame) * p.kept_capacity;
     const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536
     const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
+    const uint32_t *mb = p.mask.bits ? p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row : nullptr;
 
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
         cells[i] = kEmptyCell;
-        min_hi[i] = 0xFFFFFFFFu;
-        min_lo[i] = 0xFFFFFFFFu;
+        cmin[i] = kDeadKey;
     }
-    if (p.mask.bits != nullptr) {
-        // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66).  Candidate generation
-        // already honours the mask; this only matters where a zero response can pass a negative threshold.
-        const uint32_t *mb = p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t xy = cand_key_xy(__ldg(keys + i));
-            const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
-            alive[i] = uint8_t((mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u);
-        }
-    } else {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) alive[i] = 1;
+    if (threadIdx.x == 0) {
+        s_kept = 0u;
+        s_count[0] = 0u;
+        s_count[1] = 0u;
     }
-    if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
 
     if (d < 0) {
@@ -182,58 +184,58 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
         if (threadIdx.x == 0) s_kept = min(n, uint32_t(p.kept_capacity));
         __syncthreads();
     } else {
+        // Each round: (1) every live candidate that a point kept in the previous round covers dies (a kept point covers
+        // itself); the others post their key to their cell (64-bit atomicMin) and move to the next round's list;
+        // (2) a candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no live
+        // better-ranked candidate within d, so the sequential walk would keep it: it is kept now.
+        uint32_t m = n;          // live candidates entering the round
+        const uint32_t *cur = nullptr;   // null: round 0 walks the candidate slot itself
         for (int round = 0;; ++round) {
-            // ---- A: kill what the previous round's kept points cover; post to cells (response word) ----
-            if (threadIdx.x == 0) s_alive = 0u;
-            __syncthreads();
-            uint32_t mine_alive = 0u;
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                if (!alive[i]) continue;
-                const uint64_t key = __ldg(keys + i);
-                const uint32_t xy = cand_key_xy(key);
-                const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
-                const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
-                if (round > 0 && near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d)) {
-                    alive[i] = 0;
-                } else {
-                    atomicMin(min_hi + cy * p.cells_x + cx, uint32_t(key >> 32));
-                    ++mine_alive;
+            uint32_t *nxt = (round & 1) ? list_b : list_a;
+            uint32_t *nxt_count = &s_count[round & 1];
+            const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
+            for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
+                bool live = i < m;
+                uint32_t ci = 0u;
+                int c = 0;
+                if (live) {
+                    ci = cur ? cur[i] : i;
+                    const uint64_t key = __ldg(keys + ci);
+                    const uint32_t xy = cand_key_xy(key);
+                    const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
+                    const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
+                    c = cy * p.cells_x + cx;
+                    if (round == 0) {
+                        // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
+                        if (mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
+                    } else {
+                        live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                    }
+                    if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                 }
+                list_push(live, ci, nxt, nxt_count);
             }
-            if (mine_alive) atomicAdd(&s_alive, mine_alive);
             __syncthreads();
-            if (s_alive == 0u) break;
-            // ---- A2: among the candidates that share the cell's best response word, post the position word ----
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                if (!alive[i]) continue;
-                const uint64_t key = __ldg(keys + i);
+            m = *nxt_count;
+            if (m == 0u) break;
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                const uint32_t ci = nxt[i];
+                const uint64_t key = __ldg(keys + ci);
                 const uint32_t xy = cand_key_xy(key);
                 const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
                 const int c = cy * p.cells_x + cx;
-                if (min_hi[c] == uint32_t(key >> 32)) atomicMin(min_lo + c, xy);
-            }
-            __syncthreads();
-            // ---- B: cell winners that also beat the 8 neighbouring cells are kept ----
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                if (!alive[i]) continue;
-                const uint64_t key = __ldg(keys + i);
-                const uint32_t xy = cand_key_xy(key);
-                const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
-                const int c = cy * p.cells_x + cx;
-                if (min_hi[c] != uint32_t(key >> 32) || min_lo[c] != xy) continue;
-                if (key < neighbour_min(min_hi, min_lo, p.cells_x, p.cells_y, cx, cy)) {
-                    alive[i] = 0;
+                if (uint64_t(cmin[c]) != key) continue;
+                if (key < neighbour_min(cmin, p.cells_x, p.cells_y, cx, cy)) {
                     const uint32_t slot = atomicAdd(&s_kept, 1u);
                     if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                    cells[c] = xy;  // read by the next round, after the barriers below
+                    cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
                 }
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
-                min_hi[i] = 0xFFFFFFFFu;
-                min_lo[i] = 0xFFFFFFFFu;
-            }
-            // (the barrier at the top of the next round orders these resets and the new `cells` entries)
+            for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
+            if (threadIdx.x == 0) s_count[(round + 1) & 1] = 0u;
+            cur = nxt;
+            __syncthreads();
         }
     }
 
