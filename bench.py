@@ -266,10 +266,11 @@ def main():
     algo_bytes = n * px + int(cand_counts.sum()) * 8 + n * 4  # u8 frame in, 8-byte candidate keys + counters out
     peak, peak_src = measured_peak_gbs()
     achieved = algo_bytes / per_launch / 1e9
-    roofline = {"bound": "hbm", "kernel": "fdb::fast_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "fdb::fast_sparse_kernel (fd_fast_sparse.cu; thr 10 leaves s_min >= 7, so the sparse form runs)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": round(per_launch * 1e6, 2),
-                "note": "1 B/px kernel: issue-bound, see DESIGN.md and profiles/"}
+                "note": "1 B/px kernel: instruction-issue bound (77 % issue slots busy, ALU pipe the fullest), see DESIGN.md section 4 and "
+                        "profiles/r1_fast_sparse_brief_ncu_summary.txt; traffic = dram bytes per launch from that ncu capture"}
     prof = os.path.join(ROOT, "profiles", "fast_kernel_traffic.json")
     if os.path.exists(prof):
         try:
@@ -336,6 +337,33 @@ def main():
         s = timed(lsd_step, steps2, 2)
         extras["lsd_field (norm+angle maps, no seed sort)"] = {"mpixel_s": round(world * nl * px * steps2 / s / 1e6, 1),
                                                               "hbm_frac_9Bpx": round(nl * px * 9 * steps2 / s / 1e9 / peak, 4)}
+
+        # ---- the other BASELINE.json configs at their named shapes (small batches; parity is in tests/) -------------
+        from feature_detector_b200.synth import synth
+
+        def named(name, w2, h2, count, fn, bytes_per_px):
+            fr = np.stack([synth(w2, h2, rank * count + i) for i in range(min(count, 4))])
+            fr = np.concatenate([fr] * ((count + len(fr) - 1) // len(fr)))[:count]   # cyclic copies of 4 generated frames
+            dev_fr = torch.from_numpy(fr).to(dev)
+            ctx.bind_device(dev_fr.data_ptr(), h2, w2, count)
+            s2 = timed(fn, steps2, 2)
+            ctx.sync()
+            extras[name] = {"mpixel_s": round(world * count * w2 * h2 * steps2 / s2 / 1e6, 1), "frames_s": round(world * count * steps2 / s2, 1),
+                            "ms_per_step": round(s2 / steps2 * 1e3, 3), "frames": count,
+                            "hbm_frac": round(count * w2 * h2 * bytes_per_px * steps2 / s2 / 1e9 / peak, 4), "bytes_per_px": bytes_per_px}
+            return dev_fr
+
+        shi = fd.DetectParams(fd.SHI_TOMAS, 40.0, 20, 1000)
+        keep = named("configs[2] shi_tomas top-1000, 1280x720 x 256", 1280, 720, 256, lambda: ctx.detect(shi, 131072), 1.0)
+        extras["configs[2] shi_tomas top-1000, 1280x720 x 256"]["mean_keypoints"] = float(ctx.keypoint_counts().mean())
+        har = fd.DetectParams(fd.HARRIS, 30.0, 20, 200)
+        keep = named("configs[3] harris candidates, 3840x2160 x 16 (untiled, one GPU)", 3840, 2160, 16, lambda: ctx.compute_candidates(har, 1 << 20), 1.8)
+        extras["configs[3] harris candidates, 3840x2160 x 16 (untiled, one GPU)"]["mean_candidates"] = float(ctx.candidate_counts().mean())
+        keep = named("configs[3] harris + select, 3840x2160 x 16", 3840, 2160, 16, lambda: ctx.detect(har, 1 << 20), 1.8)
+        keep = named("configs[4] lsd field, 1920x1080 x 64", 1920, 1080, 64, lsd_step, 9.0)
+        lsd_sorted = fd.LsdParams(20.0, 1)
+        keep = named("configs[4] lsd field + seed order, 1920x1080 x 64", 1920, 1080, 64, lambda: ctx.lsd_field(lsd_sorted), 9.2)
+        del keep
 
     if rank == 0:
         line = {
