@@ -68,30 +68,36 @@ __device__ __forceinline__ void product_row(HRow &h, const PixRow &up, const Pix
     }
 }
 
+// Branch-free: the reference's early exits (harris.cpp:98, shi_tomas.cpp:96) only decide whether 0 is stored, so the
+// full expression is always evaluated (same operations, same order) and the tests pick the stored value at the end.
 template <int KIND>
 __device__ __forceinline__ float response_of(float sxx, float syy, float sxy, const CornerArgs &p) {
     if (KIND == 0) {
         const float trace = __fadd_rn(sxx, syy);                                            // harris.cpp:97
         const float tt = __fmul_rn(trace, trace);
-        if (!(__fmul_rn(__fmul_rn(tt, 0.21f), p.inv_cnt2) > p.thr)) return 0.0f;            // harris.cpp:98
+        const bool pre = __fmul_rn(__fmul_rn(tt, 0.21f), p.inv_cnt2) > p.thr;               // harris.cpp:98
         const float det = __fsub_rn(__fmul_rn(sxx, syy), __fmul_rn(sxy, sxy));
         const float res = __fmul_rn(__fsub_rn(det, __fmul_rn(__fmul_rn(p.alpha, trace), trace)), p.inv_cnt2);  // harris.cpp:100
-        return res > p.thr ? res : 0.0f;                                                    // harris.cpp:101-103
+        return (pre && res > p.thr) ? res : 0.0f;                                           // harris.cpp:101-103
     } else {
         const float a = __fmul_rn(sxx, p.inv_cnt);                                          // shi_tomas.cpp:94
         const float c = __fmul_rn(syy, p.inv_cnt);                                          // shi_tomas.cpp:95
         const float ac = __fadd_rn(a, c);
-        if (!(ac > p.thr)) return 0.0f;                                                     // shi_tomas.cpp:96
+        const bool pre = ac > p.thr;                                                        // shi_tomas.cpp:96
         const float b = __fmul_rn(sxy, p.inv_cnt);                                          // shi_tomas.cpp:97
         const float diff = __fsub_rn(a, c);                                                 // shi_tomas.cpp:98
         const float common = __fsqrt_rn(__fadd_rn(__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(4.0f, b), b)));  // shi_tomas.cpp:99
         const float res = __fmul_rn(__fadd_rn(ac, common), 0.5f);                           // shi_tomas.cpp:100
-        return res > p.thr ? res : 0.0f;
+        return (pre && res > p.thr) ? res : 0.0f;
     }
 }
 
+constexpr int CORNER_STAGE = 256;  // candidate keys staged per warp (a row adds at most 128)
+
 template <int KIND, bool MASKED>
 __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerArgs p) {
+    __shared__ uint64_t stage_all[CORNER_THREADS / 32][CORNER_STAGE];
+    uint64_t *stage = stage_all[threadIdx.x >> 5];
     const FrameView &fv = p.fv;
     const int lane = lane_id();
     const int warps_per_block = blockDim.x >> 5;
@@ -154,6 +160,17 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
         }
         uint32_t *counter = p.cand_counts + frame;
         uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
+        uint32_t n_staged = 0u;  // warp-uniform fill of the staging buffer: one global atomic per flush, not per row
+        auto flush_stage = [&]() {
+            __syncwarp();
+            uint32_t g = 0u;
+            if (lane == 0) g = atomicAdd(counter, n_staged);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            for (uint32_t i = lane; i < n_staged; i += 32)
+                if (g + i < p.cand_capacity) slot[g + i] = stage[i];
+            __syncwarp();
+            n_staged = 0u;
+        };
         float *resp_map = p.response_map ? p.response_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
         // pre-existing features: the response is only evaluated where the mask is set (harris.cpp:94), 0 elsewhere
         const uint32_t *mbits = MASKED ? p.mask.bits + int64_t(frame) * fv.rows * p.mask.words_per_row + (c0 >> 5) : nullptr;
@@ -216,14 +233,16 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                             if (col_owned[j] && v > p.thr && v > l && v > r && v > resp[cur][j] && v > rq[j]) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
-                            uint32_t pos = warp_reserve(counter, __popc(mine));
+                            uint32_t base = n_staged;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                if ((mine >> j) & 1u) {
-                                    if (pos < p.cand_capacity) slot[pos] = make_cand_key(resp[p2][j], uint32_t(m + p.tile.row_offset), uint32_t(c0 + j));
-                                    ++pos;
-                                }
+                                const uint32_t bm = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+                                if ((mine >> j) & 1u)
+                                    stage[base + __popc(bm & ((1u << lane) - 1u))] = make_cand_key(resp[p2][j], uint32_t(m + p.tile.row_offset), uint32_t(c0 + j));
+                                base += __popc(bm);
                             }
+                            n_staged = base;
+                            if (n_staged > CORNER_STAGE - 128) flush_stage();
                         }
                     }
                     // rotate: response row n-2 replaces row n-5's slot
@@ -233,6 +252,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                 }
             }
         }
+        if (n_staged != 0u) flush_stage();
     }
 }
 
