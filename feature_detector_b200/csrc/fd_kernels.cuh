@@ -95,6 +95,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
 constexpr int SELECT_THREADS = 256;
 constexpr int SELECT_SORT_SMEM = 1024;    // kept points sorted in shared memory up to this many
+constexpr int SELECT_PREFIX_MIN = 8192;   // frames with more candidates than this run the rounds on a rank prefix first
 
 struct SelectArgs {
     int rows, cols, n_frames;

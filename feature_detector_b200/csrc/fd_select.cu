@@ -151,8 +151,11 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
         cmin = reinterpret_cast<unsigned long long *>(p.cell_scratch + int64_t(frame) * ((n_cells * 3 + 1) & ~1));  // keeps 8-byte alignment
         cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     }
-    __shared__ uint32_t s_kept, s_count[2];
-    __shared__ uint64_t s_sort[SELECT_SORT_SMEM];
+    __shared__ uint32_t s_kept, s_count[2], s_admit;
+    __shared__ uint64_t s_limit;
+    // s_sort doubles as the 4096-bin (16 KiB) histogram of the rank-prefix search below
+    __shared__ uint64_t s_sort[SELECT_SORT_SMEM > 2048 ? SELECT_SORT_SMEM : 2048];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(s_sort);
 
     const uint32_t count = p.cand_counts[frame];
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
@@ -188,53 +191,118 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
         // itself); the others post their key to their cell (64-bit atomicMin) and move to the next round's list;
         // (2) a candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no live
         // better-ranked candidate within d, so the sequential walk would keep it: it is kept now.
-        uint32_t m = n;          // live candidates entering the round
-        const uint32_t *cur = nullptr;   // null: round 0 walks the candidate slot itself
-        for (int round = 0;; ++round) {
-            uint32_t *nxt = (round & 1) ? list_b : list_a;
-            uint32_t *nxt_count = &s_count[round & 1];
-            const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
-            for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
-                bool live = i < m;
-                uint32_t ci = 0u;
-                int c = 0;
-                if (live) {
-                    ci = cur ? cur[i] : i;
+        // Only the best-ranked `want` kept points are returned, and a candidate's fate depends on better-ranked candidates
+        // only, so the walk may stop at any rank prefix that already yields `want` kept points.  With many candidates the
+        // rounds therefore run on rank ranges: first the keys up to the histogram bin (top 12 key bits) that holds the K-th
+        // best key; if that keeps too few, the next range (K fourfold) is admitted against the points kept so far.  Exact,
+        // and a 4K Harris frame with 5 x 10^5 candidates and needed = 200 touches a few thousand of them.
+        uint32_t want_kept = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;
+        want_kept = min(want_kept, uint32_t(p.kp_capacity));
+        const bool by_prefix = n > SELECT_PREFIX_MIN;
+        uint32_t prefix_k = by_prefix ? max(uint32_t(SELECT_PREFIX_MIN / 2), 8u * want_kept) : n;
+        if (by_prefix) {   // histogram of the top 12 key bits, once
+            for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(hist + uint32_t(__ldg(keys + i) >> 52), 1u);
+            __syncthreads();
+        }
+        uint64_t lower = 0ull;   // keys below this were admitted by earlier batches
+        for (int batch = 0;; ++batch) {
+            uint64_t limit = kDeadKey;   // this batch admits lower <= key < limit
+            uint32_t admitted = n;       // candidates with key < limit
+            if (by_prefix && prefix_k < n) {
+                if (threadIdx.x < 32) {   // first bin at which the running count reaches prefix_k (one warp, 128 bins per lane)
+                    uint32_t mine = 0u;
+#pragma unroll 4
+                    for (int b = 0; b < 128; ++b) mine += hist[threadIdx.x * 128 + b];
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane_id() >= o) incl += v;
+                    }
+                    const uint32_t before = incl - mine;
+                    if (before < prefix_k && incl >= prefix_k) {   // exactly one lane
+                        uint32_t run = before;
+                        int b = 0;
+#pragma unroll 1
+                        for (; b < 128; ++b) {
+                            run += hist[threadIdx.x * 128 + b];
+                            if (run >= prefix_k) break;
+                        }
+                        const uint32_t bin = threadIdx.x * 128 + b;
+                        s_limit = (bin >= 4095u) ? kDeadKey : (uint64_t(bin + 1u) << 52);
+                        s_admit = (bin >= 4095u) ? n : run;
+                    }
+                }
+                __syncthreads();
+                limit = s_limit;
+                admitted = s_admit;
+                __syncthreads();
+            }
+
+            if (threadIdx.x == 0) {
+                s_count[0] = 0u;
+                s_count[1] = 0u;
+            }
+            __syncthreads();
+            uint32_t m = n;          // live candidates entering the round
+            const uint32_t *cur = nullptr;   // null: round 0 walks the candidate slot itself
+            for (int round = 0;; ++round) {
+                uint32_t *nxt = (round & 1) ? list_b : list_a;
+                uint32_t *nxt_count = &s_count[round & 1];
+                const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
+                for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
+                    bool live = i < m;
+                    uint32_t ci = 0u;
+                    int c = 0;
+                    if (live) {
+                        ci = cur ? cur[i] : i;
+                        const uint64_t key = __ldg(keys + ci);
+                        const uint32_t xy = cand_key_xy(key);
+                        const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
+                        const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
+                        c = cy * p.cells_x + cx;
+                        if (round == 0) {
+                            live = key >= lower && key < limit;
+                            // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
+                            if (live && mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
+                            // later batches start against everything the better-ranked batches kept
+                            if (live && batch > 0) live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                        } else {
+                            live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                        }
+                        if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
+                    }
+                    list_push(live, ci, nxt, nxt_count);
+                }
+                __syncthreads();
+                m = *nxt_count;
+                if (m == 0u) break;
+                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                    const uint32_t ci = nxt[i];
                     const uint64_t key = __ldg(keys + ci);
                     const uint32_t xy = cand_key_xy(key);
-                    const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
-                    const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
-                    c = cy * p.cells_x + cx;
-                    if (round == 0) {
-                        // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
-                        if (mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
-                    } else {
-                        live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                    const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
+                    const int c = cy * p.cells_x + cx;
+                    if (uint64_t(cmin[c]) != key) continue;
+                    if (key < neighbour_min(cmin, p.cells_x, p.cells_y, cx, cy)) {
+                        const uint32_t slot = atomicAdd(&s_kept, 1u);
+                        if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
+                        cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
                     }
-                    if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                 }
-                list_push(live, ci, nxt, nxt_count);
+                __syncthreads();
+                for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
+                if (threadIdx.x == 0) s_count[(round + 1) & 1] = 0u;
+                cur = nxt;
+                __syncthreads();
             }
-            __syncthreads();
-            m = *nxt_count;
-            if (m == 0u) break;
-            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                const uint32_t ci = nxt[i];
-                const uint64_t key = __ldg(keys + ci);
-                const uint32_t xy = cand_key_xy(key);
-                const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
-                const int c = cy * p.cells_x + cx;
-                if (uint64_t(cmin[c]) != key) continue;
-                if (key < neighbour_min(cmin, p.cells_x, p.cells_y, cx, cy)) {
-                    const uint32_t slot = atomicAdd(&s_kept, 1u);
-                    if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                    cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
-                }
-            }
-            __syncthreads();
-            for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
-            if (threadIdx.x == 0) s_count[(round + 1) & 1] = 0u;
-            cur = nxt;
+            // enough kept points (or every candidate admitted): done.  Otherwise admit the next, four times larger, rank range;
+            // what has been kept so far stays kept (those decisions never depend on worse-ranked candidates).
+            if (admitted >= n || s_kept >= want_kept) break;
+            lower = limit;
+            prefix_k = (prefix_k > n / 4u) ? n : prefix_k * 4u;
             __syncthreads();
         }
     }
