@@ -72,7 +72,8 @@ struct fd_context {
     bool frame_map_valid = false, frame_map_failed = false;
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted;
+    DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed;
+    size_t lsd_hist_zeroed = 0;   // bytes of lsd_hist known to be zero (the scatter kernel restores the zeros it consumes)
     float *lsd_norm_p = nullptr, *lsd_angle_p = nullptr;
     int32_t *lsd_sorted_p = nullptr, *lsd_nvalid_p = nullptr;
     bool have_lsd = false, lsd_sorted_valid = false;
@@ -524,7 +525,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -888,8 +889,18 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
             dev_sorted_idx = static_cast<int32_t *>(ctx->lsd_sorted.ptr);
         }
         FD_CUDA(ctx, cudaMemsetAsync(ctx->lsd_counts.ptr, 0, size_t(fv.n_frames) * 4, ctx->stream));
+        const size_t hist_bytes = size_t(fv.n_frames) * LSD_BINS * 4;
+        if (ctx->lsd_hist.bytes < hist_bytes) ctx->lsd_hist_zeroed = 0;
+        FD_TRY(reserve(ctx, ctx->lsd_hist, hist_bytes));
+        FD_TRY(reserve(ctx, ctx->lsd_start, hist_bytes));
+        FD_TRY(reserve(ctx, ctx->lsd_bucketed, px * fv.n_frames * 8));
+        if (ctx->lsd_hist_zeroed < hist_bytes) {
+            FD_CUDA(ctx, cudaMemsetAsync(ctx->lsd_hist.ptr, 0, ctx->lsd_hist.bytes, ctx->stream));
+            ctx->lsd_hist_zeroed = ctx->lsd_hist.bytes;
+        }
         a.seed_keys = static_cast<uint64_t *>(ctx->lsd_keys.ptr);
         a.seed_counts = static_cast<uint32_t *>(ctx->lsd_counts.ptr);
+        a.seed_hist = static_cast<uint32_t *>(ctx->lsd_hist.ptr);
     }
     const int n_strips = (fv.cols + 127) / 128;
     int grid;
@@ -897,8 +908,9 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
     FD_CUDA(ctx, launch_lsd(a, grid, ctx->stream));
     ++ctx->launches;
     if (params->want_sorted) {
-        FD_CUDA(ctx, launch_seed_sort(a.seed_keys, a.seed_counts, int64_t(px), fv.n_frames, dev_sorted_idx, fv.cols, ctx->stream));
-        ctx->launches += 2;
+        FD_CUDA(ctx, launch_seed_order(a, static_cast<uint64_t *>(ctx->lsd_bucketed.ptr), static_cast<uint32_t *>(ctx->lsd_start.ptr), dev_sorted_idx,
+                                       ctx->stream));
+        ctx->launches += 3;
         if (dev_n_valid)
             FD_CUDA(ctx, cudaMemcpyAsync(dev_n_valid, ctx->lsd_counts.ptr, size_t(fv.n_frames) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }

@@ -133,20 +133,23 @@ cudaError_t launch_brief(const BriefArgs &args, cudaStream_t stream);
 
 // ---- kernel 5: LSD gradient / level-line field --------------------------------------------------
 constexpr int LSD_THREADS = 256;
+constexpr int LSD_MAX_M = 2 * 255 * 255;   // largest ad^2 + bc^2 (feature_line_detector.cpp:76-82 on 8-bit pixels)
+constexpr int LSD_BINS = LSD_MAX_M + 1;    // one bin per attainable gradient norm
 struct LsdArgs {
     FrameView fv;
     float min_norm;
     float *norm;               // n_frames * (rows-1) * (cols-1)
     float *angle;
-    uint64_t *seed_keys;       // optional: per-frame slots of (rows-1)*(cols-1) keys
+    uint64_t *seed_keys;       // optional: per-frame slots of rows*cols keys: (m << 32) | (col << 16) | row, m = ad^2 + bc^2
     uint32_t *seed_counts;
+    uint32_t *seed_hist;       // with seed_keys: n_frames * LSD_BINS counters, zero on entry (the scatter returns them to zero)
     int n_bands, band_rows;
     int64_t n_items;
 };
 cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
-// Sort each frame's seed keys ascending and strip them to int32 map indices.
-cudaError_t launch_seed_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_frames, int32_t *sorted_idx, int map_cols,
-                             cudaStream_t stream);
+// Seed order by exact magnitude binning: scan of the histogram, scatter into buckets, order inside buckets; writes the
+// valid pixels of every frame as (row * cols + col) indices, norm descending, ties in the reference's push order.
+cudaError_t launch_seed_order(const LsdArgs &args, uint64_t *bucketed, uint32_t *start, int32_t *sorted_idx, cudaStream_t stream);
 
 // ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
 cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity, uint32_t *overflow_flag,
