@@ -98,6 +98,7 @@ template <int KIND, bool MASKED>
 __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerArgs p) {
     __shared__ uint64_t stage_all[CORNER_THREADS / 32][CORNER_STAGE];
     uint64_t *stage = stage_all[threadIdx.x >> 5];
+    uint2 *stage2 = reinterpret_cast<uint2 *>(stage);   // little endian: .x = low word of the key, .y = high word
     const FrameView &fv = p.fv;
     const int lane = lane_id();
     const int warps_per_block = blockDim.x >> 5;
@@ -233,12 +234,19 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                             if (col_owned[j] && v > p.thr && v > l && v > r && v > resp[cur][j] && v > rq[j]) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
+                            // key halves written as two 32-bit words: high = ~ordered(response), low = (row << 16) | col
+                            const uint32_t lo0 = (uint32_t(m + p.tile.row_offset) << 16) | uint32_t(c0);
+                            const uint32_t lt = (1u << lane) - 1u;
                             uint32_t base = n_staged;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint32_t bm = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
-                                if ((mine >> j) & 1u)
-                                    stage[base + __popc(bm & ((1u << lane) - 1u))] = make_cand_key(resp[p2][j], uint32_t(m + p.tile.row_offset), uint32_t(c0 + j));
+                                const bool on = (mine >> j) & 1u;
+                                const uint32_t bm = __ballot_sync(0xffffffffu, on);
+                                if (on) {
+                                    const uint32_t b = __float_as_uint(resp[p2][j]);
+                                    const uint32_t hi = b ^ ~(uint32_t(int32_t(b) >> 31) | 0x80000000u);   // ~float_to_ordered(b)
+                                    stage2[base + __popc(bm & lt)] = make_uint2(lo0 + uint32_t(j), hi);
+                                }
                                 base += __popc(bm);
                             }
                             n_staged = base;
