@@ -68,8 +68,9 @@ struct fd_context {
     TileView tile = {};
 
     // TMA view of the bound frames for the sparse FAST kernel (rebuilt when the binding changes)
-    CUtensorMap frame_map;
-    bool frame_map_valid = false, frame_map_failed = false;
+    CUtensorMap frame_map, corner_map;   // [0] box 160 x FAST_SPARSE_GROUP_ROWS (sparse FAST), [1] box 160 x CORNER_TMA_GROUP_ROWS
+    bool frame_map_valid = false, frame_map_failed = false, corner_map_valid = false, corner_map_failed = false;
+    bool force_stream_corner = false;  // FD_B200_CORNER_STREAM=1: testing knob, always take the register-streaming corner kernel
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed;
@@ -236,11 +237,14 @@ fd_status ensure_fast_tables(fd_context *ctx, uint32_t count) {
 
 // 3-D TMA map (cols x rows x frames, u8) with a 160 x 16 x 1 box for the sparse FAST kernel.  Needs 16-byte aligned base,
 // pitch and frame stride; returns false (and the dense kernel is used) when the layout or the driver does not allow it.
-bool ensure_frame_map(fd_context *ctx) {
-    if (ctx->frame_map_valid) return true;
-    if (ctx->frame_map_failed) return false;
+bool ensure_frame_map(fd_context *ctx, bool for_corner = false) {
+    bool &valid = for_corner ? ctx->corner_map_valid : ctx->frame_map_valid;
+    bool &failed = for_corner ? ctx->corner_map_failed : ctx->frame_map_failed;
+    CUtensorMap *map = for_corner ? &ctx->corner_map : &ctx->frame_map;
+    if (valid) return true;
+    if (failed) return false;
     const FrameView &fv = ctx->fv;
-    ctx->frame_map_failed = true;
+    failed = true;
     if (reinterpret_cast<uintptr_t>(fv.data) % 16 != 0 || fv.pitch % 16 != 0 || fv.frame_stride % 16 != 0) return false;
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -256,13 +260,13 @@ bool ensure_frame_map(fd_context *ctx) {
     }
     const cuuint64_t dims[3] = {cuuint64_t(fv.cols), cuuint64_t(fv.rows), cuuint64_t(fv.n_frames)};
     const cuuint64_t strides[2] = {cuuint64_t(fv.pitch), cuuint64_t(fv.frame_stride)};
-    const cuuint32_t box[3] = {160u, cuuint32_t(FAST_SPARSE_GROUP_ROWS), 1u};  // box starts are 16-byte aligned: strip * 128 - 16
+    const cuuint32_t box[3] = {160u, cuuint32_t(for_corner ? CORNER_TMA_GROUP_ROWS : FAST_SPARSE_GROUP_ROWS), 1u};  // box starts are 16-byte aligned
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = encode(&ctx->frame_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(fv.data), dims, strides, box, estr,
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(fv.data), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-    ctx->frame_map_failed = false;
-    ctx->frame_map_valid = true;
+    failed = false;
+    valid = true;
     return true;
 }
 
@@ -427,8 +431,13 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.cand_lo = std::max(a.resp_lo, tile.own_lo);
             a.cand_hi = std::max(a.cand_lo, std::min(a.resp_hi + 1, tile.own_hi));
             int grid;
-            plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
-            FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
+            if (mask.bits == nullptr && !ctx->force_stream_corner && a.cand_hi > a.cand_lo && ensure_frame_map(ctx, true)) {
+                plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_TMA_THREADS / 32, 1, 42, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                FD_CUDA(ctx, launch_corner_tma(a, &ctx->corner_map, grid, ctx->stream));
+            } else {
+                plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                FD_CUDA(ctx, launch_corner(a, grid, ctx->stream));
+            }
             ++ctx->launches;
         }
     }
@@ -513,6 +522,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
+    if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     *out_ctx = ctx;
@@ -567,7 +577,7 @@ fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows
     }
     ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, pitch, stride, n_frames, int(pitch / 4)};
     ctx->frames_bound = true;
-    ctx->frame_map_valid = ctx->frame_map_failed = false;
+    ctx->frame_map_valid = ctx->frame_map_failed = ctx->corner_map_valid = ctx->corner_map_failed = false;
     ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
     return FD_OK;
 }
@@ -590,7 +600,7 @@ fd_status fd_bind_device_frames(fd_context *ctx, const uint8_t *dev_frames, int 
         ctx->fv = FrameView{static_cast<const uint8_t *>(ctx->owned_frames.ptr), rows, cols, np, ns, n_frames, int(np / 4)};
     }
     ctx->frames_bound = true;
-    ctx->frame_map_valid = ctx->frame_map_failed = false;
+    ctx->frame_map_valid = ctx->frame_map_failed = ctx->corner_map_valid = ctx->corner_map_failed = false;
     ctx->have_candidates = ctx->have_keypoints = ctx->have_desc = ctx->have_lsd = false;
     return FD_OK;
 }

@@ -19,11 +19,13 @@
 //   * a register pipeline three rows deep: pixel row n arrives -> products of row n-1 -> response of row
 //     n-2 -> NMS of row n-3.  Nothing but the input frame is read from HBM and nothing but candidates
 //     (and, on request, the dense response map) is written.
-#include "fd_kernels.cuh"
+#include "fd_corner_common.cuh"
 
 namespace fdb {
 
 namespace {
+
+using corner::response_of;
 
 // Bias per product so that nine of them add up to the bit pattern of a float whose value is
 // (sum + kSumBase): 9 * kBiasPos = 0x4B000006 -> float(2^23 + 6 + sum)      (sum >= 0)
@@ -65,30 +67,6 @@ __device__ __forceinline__ void product_row(HRow &h, const PixRow &up, const Pix
         h.xx[j] = pxx[j] + pxx[j + 1] + pxx[j + 2];
         h.yy[j] = pyy[j] + pyy[j + 1] + pyy[j + 2];
         h.xy[j] = pxy[j] + pxy[j + 1] + pxy[j + 2];
-    }
-}
-
-// Branch-free: the reference's early exits (harris.cpp:98, shi_tomas.cpp:96) only decide whether 0 is stored, so the
-// full expression is always evaluated (same operations, same order) and the tests pick the stored value at the end.
-template <int KIND>
-__device__ __forceinline__ float response_of(float sxx, float syy, float sxy, const CornerArgs &p) {
-    if (KIND == 0) {
-        const float trace = __fadd_rn(sxx, syy);                                            // harris.cpp:97
-        const float tt = __fmul_rn(trace, trace);
-        const bool pre = __fmul_rn(__fmul_rn(tt, 0.21f), p.inv_cnt2) > p.thr;               // harris.cpp:98
-        const float det = __fsub_rn(__fmul_rn(sxx, syy), __fmul_rn(sxy, sxy));
-        const float res = __fmul_rn(__fsub_rn(det, __fmul_rn(__fmul_rn(p.alpha, trace), trace)), p.inv_cnt2);  // harris.cpp:100
-        return (pre && res > p.thr) ? res : 0.0f;                                           // harris.cpp:101-103
-    } else {
-        const float a = __fmul_rn(sxx, p.inv_cnt);                                          // shi_tomas.cpp:94
-        const float c = __fmul_rn(syy, p.inv_cnt);                                          // shi_tomas.cpp:95
-        const float ac = __fadd_rn(a, c);
-        const bool pre = ac > p.thr;                                                        // shi_tomas.cpp:96
-        const float b = __fmul_rn(sxy, p.inv_cnt);                                          // shi_tomas.cpp:97
-        const float diff = __fsub_rn(a, c);                                                 // shi_tomas.cpp:98
-        const float common = __fsqrt_rn(__fadd_rn(__fmul_rn(diff, diff), __fmul_rn(__fmul_rn(4.0f, b), b)));  // shi_tomas.cpp:99
-        const float res = __fmul_rn(__fadd_rn(ac, common), 0.5f);                           // shi_tomas.cpp:100
-        return (pre && res > p.thr) ? res : 0.0f;
     }
 }
 

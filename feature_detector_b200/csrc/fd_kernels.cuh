@@ -89,6 +89,11 @@ struct CornerArgs {
     int cand_lo, cand_hi;     // local rows that may emit candidates: [cand_lo, cand_hi)
 };
 cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream);
+// TMA form (fd_corner_tma.cu): needs a 3-D TMA map of the frames with a 160 x CORNER_TMA_GROUP_ROWS x 1 box, and no mask.
+constexpr int CORNER_TMA_THREADS = 512;
+constexpr int CORNER_TMA_GROUP_ROWS = 12;
+size_t corner_tma_smem_bytes();
+cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, int grid, cudaStream_t stream);
 
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
 constexpr int SORT_THREADS = 256;
