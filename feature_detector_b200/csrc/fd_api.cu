@@ -470,14 +470,14 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     const int cell = std::max(p->min_feature_distance, 0) + 1;
     a.cells_x = (fv.cols + cell - 1) / cell;
     a.cells_y = (fv.rows + cell - 1) / cell;
-    const size_t cell_bytes = size_t(a.cells_x) * a.cells_y * 4;
+    const size_t cell_bytes = size_t(a.cells_x + 2) * (a.cells_y + 2) * 4;   // the grid carries a one-cell empty border
     a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
     a.cells_in_smem = cell_bytes * 3 <= 24 * 1024;
     if (!a.cells_in_smem) {
         FD_TRY(reserve(ctx, ctx->cells, (cell_bytes * 3 + 4) * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
-    a.kept_capacity = a.cells_x * a.cells_y;
+    a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
     FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 8));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
     a.live_scratch = static_cast<uint32_t *>(ctx->alive.ptr);

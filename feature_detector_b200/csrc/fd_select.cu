@@ -92,34 +92,37 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(uint64_t *keys, cons
     }
 }
 
-// Is (x, y) within Chebyshev distance d of a point stored in the 3x3 cells around (cx, cy)?
-__device__ __forceinline__ bool near_kept(const uint32_t *cells, int cells_x, int cells_y, int cx, int cy, int x, int y, int d) {
-    const int x0 = max(cx - 1, 0), x2 = min(cx + 1, cells_x - 1);
-    const int y0 = max(cy - 1, 0) * cells_x, y1 = cy * cells_x, y2 = min(cy + 1, cells_y - 1) * cells_x;
-    uint32_t q[9];
-    q[0] = cells[y0 + x0]; q[1] = cells[y0 + cx]; q[2] = cells[y0 + x2];
-    q[3] = cells[y1 + x0]; q[4] = cells[y1 + cx]; q[5] = cells[y1 + x2];
-    q[6] = cells[y2 + x0]; q[7] = cells[y2 + cx]; q[8] = cells[y2 + x2];
+// The cell grid carries a one-cell border (pitch = cells_x + 2, cell (cx, cy) at (cy + 1) * pitch + cx + 1) that stays
+// empty, so the 3x3 neighbourhood of any cell can be read without bounds tests.
+//
+// Is (x, y) within Chebyshev distance d of a point kept in the 3x3 cells around cell index c?  A kept point is stored as
+// (y << 16) | x; "both coordinates inside [x-d, x+d] x [y-d, y+d]" is one packed clamp: clamp(q, lo, hi) == q on 16-bit
+// halves (VIMNMX.U16x2).  The upper bounds stop at 65534, which no coordinate of a frame of at most 65535 columns / rows
+// exceeds, so the empty marker 0xFFFFFFFF is never inside the box.
+__device__ __forceinline__ bool near_kept(const uint32_t *cells, int pitch, int c, int x, int y, int d) {
+    const uint32_t lo = (uint32_t(max(y - d, 0)) << 16) | uint32_t(max(x - d, 0));
+    const uint32_t hi = (uint32_t(min(y + d, 65534)) << 16) | uint32_t(min(x + d, 65534));
     bool hit = false;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int qx = int(q[t] & 0xFFFFu), qy = int(q[t] >> 16);
-        hit |= (q[t] != kEmptyCell) && (abs(qx - x) <= d) && (abs(qy - y) <= d);
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const uint32_t q = cells[c + dy * pitch + dx];
+            hit |= (__vminu2(__vmaxu2(q, lo), hi) == q);
+        }
     }
     return hit;
 }
 
-// Best (smallest) key posted to the 3x3 cells around (cx, cy), the centre cell excluded.
-__device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin, int cells_x, int cells_y, int cx, int cy) {
+// Best (smallest) key posted to the 8 cells around cell index c.
+__device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin, int pitch, int c) {
     uint64_t best = kDeadKey;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
 #pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
             if (dx == 0 && dy == 0) continue;
-            const int xx = cx + dx, yy = cy + dy;
-            if (xx < 0 || yy < 0 || xx >= cells_x || yy >= cells_y) continue;
-            best = min(best, uint64_t(cmin[yy * cells_x + xx]));
+            best = min(best, uint64_t(cmin[c + dy * pitch + dx]));
         }
     }
     return best;
@@ -140,7 +143,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
     extern __shared__ __align__(16) uint8_t smem[];
     const int frame = blockIdx.x;
     const int d = p.min_distance;
-    const int n_cells = p.cells_x * p.cells_y;
+    const int pitch = p.cells_x + 2;                  // one-cell empty border all round
+    const int n_cells = pitch * (p.cells_y + 2);
     // per-cell state, shared (or, for very fine grids, global): best live key posted this round, and the kept point
     unsigned long long *cmin;
     uint32_t *cells;
@@ -262,15 +266,15 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
                         const uint32_t xy = cand_key_xy(key);
                         const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                         const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
-                        c = cy * p.cells_x + cx;
+                        c = (cy + 1) * pitch + cx + 1;
                         if (round == 0) {
                             live = key >= lower && key < limit;
                             // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
                             if (live && mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
                             // later batches start against everything the better-ranked batches kept
-                            if (live && batch > 0) live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                            if (live && batch > 0) live = !near_kept(cells, pitch, c, x, y, d);
                         } else {
-                            live = !near_kept(cells, p.cells_x, p.cells_y, cx, cy, x, y, d);
+                            live = !near_kept(cells, pitch, c, x, y, d);
                         }
                         if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                     }
@@ -284,9 +288,9 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
                     const uint64_t key = __ldg(keys + ci);
                     const uint32_t xy = cand_key_xy(key);
                     const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
-                    const int c = cy * p.cells_x + cx;
+                    const int c = (cy + 1) * pitch + cx + 1;
                     if (uint64_t(cmin[c]) != key) continue;
-                    if (key < neighbour_min(cmin, p.cells_x, p.cells_y, cx, cy)) {
+                    if (key < neighbour_min(cmin, pitch, c)) {
                         const uint32_t slot = atomicAdd(&s_kept, 1u);
                         if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
                         cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
@@ -344,7 +348,7 @@ cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t 
     return cudaGetLastError();
 }
 
-size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? size_t(a.cells_x) * a.cells_y * 12 : 0; }
+size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? size_t(a.cells_x + 2) * (a.cells_y + 2) * 12 : 0; }
 
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(args);
