@@ -131,10 +131,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    sample = min(args.frames, max(threads * 4, 64))
+    sample = min(args.frames, 1024)   # one step = the whole batch (about a second on 16 host threads)
     frames = make_frames(sample, 0)
     for _ in range(args.warmup):
-        cpu_reference_mpx(frames[:max(threads, 8)], args.fast_n, threads)
+        cpu_reference_mpx(frames[:max(threads * 2, 16)], args.fast_n, threads)
     t0 = time.perf_counter()
     kind = "port"
     for _ in range(args.steps):
@@ -187,13 +187,21 @@ def main():
     cpu = None
     if rank == 0 and world == 1:
         threads = host_threads()
-        sample = min(args.frames, max(64, threads * 4))
-        mpx, kind, sec, totals = cpu_reference_mpx(frames[:sample], args.fast_n, threads)
-        cpu = {"value": round(mpx, 3), "unit": "Mpixel/s", "cores": threads, "kind": kind,
-               "sample": f"first {sample} frames of the batch, {threads} host threads (one detector per thread), {sec:.2f} s; "
-                         f"{int(totals[0])} keypoints, {int(totals[1])} candidates"}
-        mpx1, _, sec1, _ = cpu_reference_mpx(frames[:max(8, sample // max(threads, 1))], args.fast_n, 1)
+        sample = args.frames                      # the whole batch, three times: ~3 s wall, ~50 core-seconds on 16 threads
+        cpu_reference_mpx(frames[:max(threads * 2, 16)], args.fast_n, threads)   # warm the thread pool / page the frames in
+        best, kind, totals, secs = 0.0, "port", (0, 0), []
+        for _ in range(3):
+            mpx, kind, sec, totals = cpu_reference_mpx(frames[:sample], args.fast_n, threads)
+            best = max(best, mpx)
+            secs.append(sec)
+        cpu = {"value": round(best, 3), "unit": "Mpixel/s", "cores": threads, "kind": kind,
+               "sample": f"all {sample} frames of the batch, best of 3 passes ({', '.join(f'{x:.2f}' for x in secs)} s), {threads} host threads "
+                         f"(one detector object per thread: the reference itself is single-threaded); {int(totals[0])} keypoints, "
+                         f"{int(totals[1])} candidates"}
+        n1 = min(sample, 128)
+        mpx1, _, sec1, _ = cpu_reference_mpx(frames[:n1], args.fast_n, 1)
         cpu["single_thread_mpixel_s"] = round(mpx1, 3)
+        cpu["single_thread_sample"] = f"first {n1} frames, {sec1:.2f} s"
 
     import torch
     import torch.distributed as dist
