@@ -131,10 +131,14 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    sample = min(args.frames, 1024)   # one step = the whole batch (about a second on 16 host threads)
-    frames = make_frames(sample, 0)
-    for _ in range(args.warmup):
-        cpu_reference_mpx(frames[:max(threads * 2, 16)], args.fast_n, threads)
+    # A step is a bounded sample of the batch, sized from a warm-up measurement so that the K timed steps take about a minute.
+    probe = make_frames(min(args.frames, max(threads * 4, 64)), 0)
+    t0 = time.perf_counter()
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_mpx(probe, args.fast_n, threads)
+    fps = max(args.warmup, 1) * len(probe) / max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(args.frames, max(threads, 60.0 * fps / max(args.steps, 1))))
+    frames = make_frames(args.frames, 0)[:sample]
     t0 = time.perf_counter()
     kind = "port"
     for _ in range(args.steps):
@@ -165,7 +169,7 @@ def workload_config(args, frames_per_step):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500, help="timed steps (0.8 ms each at N=1: the default keeps the timed region long enough to sample clocks)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
@@ -240,15 +244,19 @@ def main():
         ctx.detect(det, CAND_CAPACITY)
         ctx.describe_selected(brief)
 
+    timed_launches = [0]
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
+        timed_launches[0] = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
+        timed_launches[0] = ctx.launch_count - timed_launches[0]   # kernels launched inside the timed region
         barrier()
         return max_over_ranks(e0.elapsed_time(e1) / 1e3)
 
@@ -256,9 +264,8 @@ def main():
     ctx.bind_device(d_frames.data_ptr(), H, W, n)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ctx.launch_count
     sec = timed(device_step, args.steps, args.warmup)
-    launches = ctx.launch_count - l0
+    launches = timed_launches[0]
     clocks = sampler.stop()
     ctx.sync()  # raises if a candidate slot overflowed
     kp_counts = ctx.keypoint_counts()
@@ -320,7 +327,7 @@ def main():
     extras = {}
     if not args.no_extras:
         ctx.bind_device(d_frames.data_ptr(), H, W, n)
-        steps2 = max(3, args.steps // 2)
+        steps2 = max(3, min(args.steps // 2, 100))
 
         def measure(name, params, cap, with_brief):
             def step():
