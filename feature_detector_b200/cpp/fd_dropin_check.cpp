@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "descriptor_brief.h"
+#include "feature_line_detector.h"
 #include "feature_line_field.h"
 #include "feature_point_fast_detector.h"
 #include "feature_point_harris_detector.h"
@@ -180,6 +181,16 @@ int main(int argc, char **argv) {
                     "\"angle_sum\": %.6f, \"sorted_norm_hash\": \"%s\", \"descending\": %s, \"positions_ok\": %s}",
                     ok ? "true" : "false", pixels.rows(), pixels.cols(), static_cast<long long>(n_valid), sorted.size(), Hex(hn.h).c_str(), norm_sum, angle_sum,
                     Hex(hs.h).c_str(), descending ? "true" : "false", positions_ok ? "true" : "false");
+    }
+    {   // test_feature_line_detector.cpp:99-106: the whole detector, N = 200, default options
+        FeatureLineDetector detector;
+        std::vector<Vec4> lines;
+        const bool ok = detector.DetectGoodFeatures(image, 200, lines);
+        std::printf(",\n \"lsd_detect\": {\"ok\": %s, \"n_lines\": %zu, \"n_rectangles\": %zu, \"n_seeds\": %zu, \"lines\": [", ok ? "true" : "false",
+                    lines.size(), detector.rectangles().size(), detector.sorted_pixels().size());
+        for (size_t i = 0; i < lines.size(); ++i)
+            std::printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", double(lines[i][0]), double(lines[i][1]), double(lines[i][2]), double(lines[i][3]));
+        std::printf("]}");
     }
     std::printf("}\n");
     return 0;

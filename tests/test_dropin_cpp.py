@@ -49,12 +49,12 @@ def test_dropin_has_no_cpu_path(dropin_output):
         pytest.skip("GPU present: covered by the gpu-marked test")
     out = dropin_output
     assert out["fast_demo"]["ok"] is False and out["harris_demo"]["ok"] is False and out["brief_harris10"]["ok"] is False
-    assert out["lsd_field"]["ok"] is False and out["fast_demo"]["n_feat"] == 0
+    assert out["lsd_field"]["ok"] is False and out["fast_demo"]["n_feat"] == 0 and out["lsd_detect"]["ok"] is False
     assert out["null_image_returns"] is False
 
 
 @pytest.mark.gpu
-def test_dropin_replays_reference_demos(dropin_output, kat):
+def test_dropin_replays_reference_demos(dropin_output, kat, image_png):
     out = dropin_output
     gold = {(c["detector"], c["thr"]): c for c in kat["cases"] if c["frame"] == "image" and "thr" in c}
     for label, key, name in (("fast_demo", ("fast", 10.0), "Fast"), ("harris_demo", ("harris", 30.0), "Harris"), ("shi_demo", ("shi", 40.0), "Shi-Tomas"),
@@ -87,3 +87,14 @@ def test_dropin_replays_reference_demos(dropin_output, kat):
     assert l["n_valid"] == l["n_sorted"] == g["n_valid"] and l["norm_hash"] == g["norm_hash"] and l["sorted_norm_hash"] == g["sorted_norm_hash"]
     assert abs(l["norm_sum"] - g["norm_sum"]) < 1e-3 and abs(l["angle_sum"] - g["angle_sum"]) < 1e-5 * g["n_valid"]
     assert l["descending"] is True and l["positions_ok"] is True
+
+    # the whole line detector (dense stage on the GPU, host stage in feature_detector_b200/cpp/line_segments_host.cpp):
+    # 40 segments on image.png, and exactly the reference's where its build is available
+    d = out["lsd_detect"]
+    assert d["ok"] is True and d["n_lines"] == d["n_rectangles"] == 40 and d["n_seeds"] == 10087
+    from oracle.bindings import Ref, have_ref
+    if have_ref():
+        ok, ref_lines = Ref().lsd_detect(image_png, 200)
+        mine = np.array(d["lines"], np.float32).reshape(-1, 4)
+        assert ok and mine.shape == ref_lines.shape
+        assert np.array_equal(mine, ref_lines)      # same segments, same order, same bits
