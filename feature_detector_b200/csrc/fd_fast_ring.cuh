@@ -66,17 +66,6 @@ __device__ __forceinline__ void ring_step(const Row &r, const __half2 (&nhi)[2],
     }
 }
 
-// Offset table lookup: bit pattern of the reference's running float `offset` for masked-in pixel index k
-// (binary search over the <= 64 linear pieces; only candidate-bearing rows get here).
-__device__ __forceinline__ uint32_t offset_bits(const OffsetSeg *__restrict__ segs, int n_seg, uint32_t k) {
-    int lo = 0, hi = n_seg - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (segs[mid].k_start <= k) lo = mid; else hi = mid - 1;
-    }
-    return segs[lo].bits_start + (k - segs[lo].k_start) * segs[lo].step;
-}
-
 template <bool PRECHECK>
 __device__ __forceinline__ void fast_step(const Row &rm3, const Row &rm2, const Row &rm1, const Row &r0, const Row &rp1, const Row &rp2,
                                           const Row &rp3, __half2 diff2, const uint8_t *__restrict__ lut, int prune, uint32_t &scores_packed) {
