@@ -258,6 +258,42 @@ def test_lsd_field_vs_checker(ctx, checker, frames):
         assert len(np.unique(g["sorted_idx"])) == len(g["sorted_idx"])
 
 
+def _gradient_pair_image():
+    """Every (|ad|, |bc|) pair of feature_line_detector.cpp:76-79 on 8-bit pixels: at even columns of even rows the 2x2
+    neighbourhood is [[0, B], [0, D]] with B = column / 2 and D = row / 2, so ad = D and bc = B."""
+    im = np.zeros((514, 516), np.uint8)
+    b = (np.arange(516) // 2).clip(0, 255).astype(np.uint8)
+    d = (np.arange(514) // 2).clip(0, 255).astype(np.uint8)
+    im[0::2, 1::2] = b[1::2][None, :]
+    im[1::2, 1::2] = d[1::2][:, None]
+    return im
+
+
+def test_lsd_norm_every_gradient_pair(ctx, checker):
+    """The norm kernel's own square root (reciprocal-sqrt seed + one fused residual step) must round exactly like sqrtf
+    for every attainable ad^2 + bc^2; odd widths take the scalar store path, min_norm 0 makes nearly every pixel valid."""
+    im = _gradient_pair_image()
+    ad = im[1:, 1:].astype(np.int32) - im[:-1, :-1]
+    bc = im[:-1, 1:].astype(np.int32) - im[1:, :-1]
+    pairs = set(zip(np.abs(ad[1:-1, 1:-1]).ravel().tolist(), np.abs(bc[1:-1, 1:-1]).ravel().tolist()))
+    assert len(pairs) >= 256 * 256
+    for img, thr in ((im, 20.0), (im[:, :515], 0.0), (np.ascontiguousarray(im.T), 300.0)):
+        img = np.ascontiguousarray(img)
+        h, w = img.shape
+        ctx.upload(img)
+        ctx.lsd_field(fd.LsdParams(thr, 1))
+        g = ctx.lsd_download(0)
+        o = checker.lsd_map(img, thr)
+        norm, angle = g["norm"][:h - 1, :w - 1], g["angle"][:h - 1, :w - 1]
+        assert np.array_equal(norm.view(np.uint32), o["norm"].view(np.uint32))
+        valid = o["valid"].astype(bool)
+        assert g["n_valid"] == int(valid.sum())
+        assert not angle[~valid].any()
+        assert np.max(np.abs(angle[valid] - o["angle"][valid]), initial=0.0) <= 1e-5
+        rows_, cols_ = g["sorted_idx"] // w, g["sorted_idx"] % w
+        assert np.array_equal(norm[rows_, cols_], o["norm"][o["sorted_rc"][:, 0], o["sorted_rc"][:, 1]])
+
+
 def test_bound_device_frames_with_pitch(ctx, checker, torch_cuda):
     """Frames that already live on the device, including an unaligned pitch (re-pitched internally)."""
     from feature_detector_b200.synth import synth_batch
