@@ -73,7 +73,7 @@ struct fd_context {
     bool force_stream_corner = false;  // FD_B200_CORNER_STREAM=1: testing knob, always take the register-streaming corner kernel
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed;
+    DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed, lsd_item_counts, lsd_chunk_sum;
     size_t lsd_hist_zeroed = 0;   // bytes of lsd_hist known to be zero (the scatter kernel restores the zeros it consumes)
     float *lsd_norm_p = nullptr, *lsd_angle_p = nullptr;
     int32_t *lsd_sorted_p = nullptr, *lsd_nvalid_p = nullptr;
@@ -535,7 +535,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -891,8 +891,13 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
     a.min_norm = params->min_valid_gradient_norm;
     a.norm = dev_norm;
     a.angle = dev_angle;
+    const int n_strips = (fv.cols + 127) / 128;
+    int grid;
+    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 3, 16, 2, a.band_rows, a.n_bands, a.n_items, grid);
     if (params->want_sorted) {
-        FD_TRY(reserve(ctx, ctx->lsd_keys, px * fv.n_frames * 8));
+        FD_TRY(reserve(ctx, ctx->lsd_keys, size_t(a.n_items) * a.band_rows * 128 * 8));
+        FD_TRY(reserve(ctx, ctx->lsd_item_counts, size_t(a.n_items) * 4));
+        FD_TRY(reserve(ctx, ctx->lsd_chunk_sum, lsd_chunk_sum_bytes(fv.n_frames)));
         FD_TRY(reserve(ctx, ctx->lsd_counts, size_t(fv.n_frames) * 4));
         if (!dev_sorted_idx) {
             FD_TRY(reserve(ctx, ctx->lsd_sorted, px * fv.n_frames * 4));
@@ -911,16 +916,14 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
         a.seed_keys = static_cast<uint64_t *>(ctx->lsd_keys.ptr);
         a.seed_counts = static_cast<uint32_t *>(ctx->lsd_counts.ptr);
         a.seed_hist = static_cast<uint32_t *>(ctx->lsd_hist.ptr);
+        a.item_counts = static_cast<uint32_t *>(ctx->lsd_item_counts.ptr);
     }
-    const int n_strips = (fv.cols + 127) / 128;
-    int grid;
-    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 4, 8, 1, a.band_rows, a.n_bands, a.n_items, grid);
     FD_CUDA(ctx, launch_lsd(a, grid, ctx->stream));
     ++ctx->launches;
     if (params->want_sorted) {
-        FD_CUDA(ctx, launch_seed_order(a, static_cast<uint64_t *>(ctx->lsd_bucketed.ptr), static_cast<uint32_t *>(ctx->lsd_start.ptr), dev_sorted_idx,
-                                       ctx->stream));
-        ctx->launches += 3;
+        FD_CUDA(ctx, launch_seed_order(a, static_cast<uint64_t *>(ctx->lsd_bucketed.ptr), static_cast<uint32_t *>(ctx->lsd_start.ptr),
+                                       static_cast<uint32_t *>(ctx->lsd_chunk_sum.ptr), dev_sorted_idx, ctx->stream));
+        ctx->launches += LSD_SEED_ORDER_LAUNCHES;
         if (dev_n_valid)
             FD_CUDA(ctx, cudaMemcpyAsync(dev_n_valid, ctx->lsd_counts.ptr, size_t(fv.n_frames) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }

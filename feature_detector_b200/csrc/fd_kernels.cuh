@@ -145,8 +145,9 @@ struct LsdArgs {
     float min_norm;
     float *norm;               // n_frames * (rows-1) * (cols-1)
     float *angle;
-    uint64_t *seed_keys;       // optional: per-frame slots of rows*cols keys: (m << 32) | (col << 16) | row, m = ad^2 + bc^2
-    uint32_t *seed_counts;
+    uint64_t *seed_keys;       // optional: one region of band_rows * 128 keys per work item: (m << 32) | (col << 16) | row, m = ad^2 + bc^2
+    uint32_t *item_counts;     // with seed_keys: keys in each work item's region
+    uint32_t *seed_counts;     // with seed_keys: valid pixels per frame, zero on entry
     uint32_t *seed_hist;       // with seed_keys: n_frames * LSD_BINS counters, zero on entry (the scatter returns them to zero)
     int n_bands, band_rows;
     int64_t n_items;
@@ -154,7 +155,9 @@ struct LsdArgs {
 cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
 // Seed order by exact magnitude binning: scan of the histogram, scatter into buckets, order inside buckets; writes the
 // valid pixels of every frame as (row * cols + col) indices, norm descending, ties in the reference's push order.
-cudaError_t launch_seed_order(const LsdArgs &args, uint64_t *bucketed, uint32_t *start, int32_t *sorted_idx, cudaStream_t stream);
+constexpr int LSD_SEED_ORDER_LAUNCHES = 4;
+size_t lsd_chunk_sum_bytes(int n_frames);
+cudaError_t launch_seed_order(const LsdArgs &args, uint64_t *bucketed, uint32_t *start, uint32_t *chunk_sum, int32_t *sorted_idx, cudaStream_t stream);
 
 // ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
 cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity, uint32_t *overflow_flag,
