@@ -478,9 +478,9 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
     }
     a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
-    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 8));
+    FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 16));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
-    a.live_scratch = static_cast<uint32_t *>(ctx->alive.ptr);
+    a.live_scratch = static_cast<uint64_t *>(ctx->alive.ptr);
     a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;

@@ -113,7 +113,7 @@ struct SelectArgs {
     float4 *keypoints;              // n_frames slots of kp_capacity (x, y, response, 0)
     int32_t *kp_counts;
     int kp_capacity;
-    uint32_t *live_scratch;         // n_frames * 2 * cand_capacity: the live-candidate index lists of two consecutive rounds
+    uint64_t *live_scratch;         // n_frames * 2 * cand_capacity: the live-candidate key lists of two consecutive rounds
     uint64_t *kept_keys;            // n_frames slots of kept_capacity keys (the kept set before the cut)
     int kept_capacity;              // = number of grid cells (at most one kept point per cell)
     uint32_t *cell_scratch;         // global fallback for the per-cell state (3 words per cell per frame, 8-byte aligned), may be null

@@ -128,8 +128,8 @@ __device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin
     return best;
 }
 
-// Unordered append of this thread's surviving candidate index to a list (warp-aggregated counter bump).
-__device__ __forceinline__ void list_push(bool keep, uint32_t value, uint32_t *list, uint32_t *counter) {
+// Unordered append of this thread's surviving candidate key to a list (warp-aggregated counter bump).
+__device__ __forceinline__ void list_push(bool keep, uint64_t value, uint64_t *list, uint32_t *counter) {
     const uint32_t m = __ballot_sync(__activemask(), keep);
     if (m == 0u) return;
     const int leader = __ffs(m) - 1;
@@ -165,9 +165,10 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
-    // two index lists (live candidates of the current / next round), ping-pong
-    uint32_t *list_a = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
-    uint32_t *list_b = list_a + p.cand_capacity;
+    // two key lists (live candidates of the current / next round), ping-pong: rounds read their candidates with one
+    // coalesced load instead of an index and a gather
+    uint64_t *list_a = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
+    uint64_t *list_b = list_a + p.cand_capacity;
     uint64_t *kept = p.kept_keys + int64_t(frame) * p.kept_capacity;
     const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536
     const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
@@ -258,18 +259,17 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
             }
             __syncthreads();
             uint32_t m = n;          // live candidates entering the round
-            const uint32_t *cur = nullptr;   // null: round 0 walks the candidate slot itself
+            const uint64_t *cur = keys;      // round 0 walks the candidate slot itself
             for (int round = 0;; ++round) {
-                uint32_t *nxt = (round & 1) ? list_b : list_a;
+                uint64_t *nxt = (round & 1) ? list_b : list_a;
                 uint32_t *nxt_count = &s_count[round & 1];
                 const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
                 for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
                     bool live = i < m;
-                    uint32_t ci = 0u;
+                    uint64_t key = 0ull;
                     int c = 0;
                     if (live) {
-                        ci = cur ? cur[i] : i;
-                        const uint64_t key = __ldg(keys + ci);
+                        key = cur[i];
                         const uint32_t xy = cand_key_xy(key);
                         const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                         const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
@@ -285,14 +285,13 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
                         }
                         if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                     }
-                    list_push(live, ci, nxt, nxt_count);
+                    list_push(live, key, nxt, nxt_count);
                 }
                 __syncthreads();
                 m = *nxt_count;
                 if (m == 0u) break;
                 for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                    const uint32_t ci = nxt[i];
-                    const uint64_t key = __ldg(keys + ci);
+                    const uint64_t key = nxt[i];
                     const uint32_t xy = cand_key_xy(key);
                     const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
                     const int c = (cy + 1) * pitch + cx + 1;
