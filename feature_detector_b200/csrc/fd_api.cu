@@ -71,6 +71,7 @@ struct fd_context {
     CUtensorMap frame_map, corner_map;   // [0] box 160 x FAST_SPARSE_GROUP_ROWS (sparse FAST), [1] box 160 x CORNER_TMA_GROUP_ROWS
     bool frame_map_valid = false, frame_map_failed = false, corner_map_valid = false, corner_map_failed = false;
     bool force_stream_corner = false;  // FD_B200_CORNER_STREAM=1: testing knob, always take the register-streaming corner kernel
+    uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed, lsd_item_counts, lsd_chunk_sum;
@@ -463,6 +464,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.cand_capacity = capacity;
     a.min_distance = p->min_feature_distance;
     a.needed = p->needed_feature_num;
+    a.cells_min = ctx->select_cells_min;
     a.existing_counts = ctx->have_existing ? static_cast<const int32_t *>(ctx->existing_counts.ptr) : nullptr;
     a.keypoints = static_cast<float4 *>(ctx->kp.ptr);
     a.kp_counts = static_cast<int32_t *>(ctx->kp_counts.ptr);
@@ -470,12 +472,13 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     const int cell = std::max(p->min_feature_distance, 0) + 1;
     a.cells_x = (fv.cols + cell - 1) / cell;
     a.cells_y = (fv.rows + cell - 1) / cell;
-    const size_t cell_bytes = size_t(a.cells_x + 2) * (a.cells_y + 2) * 4;   // the grid carries a one-cell empty border
+    const size_t cell_bytes = select_cell_bytes(a.cells_x, a.cells_y);   // the grid carries a one-cell empty border
     a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
-    a.cells_in_smem = cell_bytes * 3 <= 24 * 1024;
+    a.cells_in_smem = cell_bytes <= 48 * 1024;
     if (!a.cells_in_smem) {
-        FD_TRY(reserve(ctx, ctx->cells, (cell_bytes * 3 + 4) * fv.n_frames));
+        FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
+        a.cell_stride = int64_t(cell_bytes);
     }
     a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
     FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 16));
@@ -485,7 +488,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;
     FD_CUDA(ctx, launch_select(a, ctx->stream));
-    ++ctx->launches;
+    ctx->launches += (a.cand_capacity > a.cells_min) ? 2 : 1;   // the per-cell form is launched only when the capacity admits it
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
     ctx->select_frames = fv.n_frames;
@@ -523,6 +526,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     ctx->stream = ctx->own_stream;
     if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
+    if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     *out_ctx = ctx;

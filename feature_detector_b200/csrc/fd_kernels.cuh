@@ -98,8 +98,10 @@ cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, in
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
-constexpr int SELECT_THREADS = 256;
+constexpr int SELECT_THREADS = 256;        // per-frame CTA when the cell grid fits shared memory
+constexpr int SELECT_MAX_THREADS = 1024;   // ... and when it lives in global memory (very fine grids: thousands of cells per round)
 constexpr int SELECT_SORT_SMEM = 1024;    // kept points sorted in shared memory up to this many
+constexpr int SELECT_CELLS_MIN = 65536;   // frames with more candidates than this group them by cell and run the rounds per cell
 constexpr int SELECT_PREFIX_MIN = 8192;   // frames with more candidates than this run the rounds on a rank prefix first
 
 struct SelectArgs {
@@ -109,6 +111,7 @@ struct SelectArgs {
     uint32_t cand_capacity;
     int min_distance;
     uint32_t needed;
+    uint32_t cells_min;             // frames with more candidates than this run the rounds per cell (SELECT_CELLS_MIN)
     const int32_t *existing_counts; // per frame, may be null (= 0)
     float4 *keypoints;              // n_frames slots of kp_capacity (x, y, response, 0)
     int32_t *kp_counts;
@@ -116,13 +119,15 @@ struct SelectArgs {
     uint64_t *live_scratch;         // n_frames * 2 * cand_capacity: the live-candidate key lists of two consecutive rounds
     uint64_t *kept_keys;            // n_frames slots of kept_capacity keys (the kept set before the cut)
     int kept_capacity;              // = number of grid cells (at most one kept point per cell)
-    uint32_t *cell_scratch;         // global fallback for the per-cell state (3 words per cell per frame, 8-byte aligned), may be null
+    uint32_t *cell_scratch;         // global fallback for the per-cell state (select_cell_bytes() per frame), may be null
+    int64_t cell_stride;            // bytes between the per-cell states of consecutive frames in cell_scratch
     int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
     uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
 };
+size_t select_cell_bytes(int cells_x, int cells_y);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
 
 // ---- kernel 4: steered BRIEF --------------------------------------------------------------------

@@ -139,50 +139,82 @@ __device__ __forceinline__ void list_push(bool keep, uint64_t value, uint64_t *l
     if (keep) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
 }
 
-__global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs p) {
+// Exclusive prefix sum of one value per thread over the whole CTA (up to 1024 threads).
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= o) incl += u;
+    }
+    if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane_id() >= o) wi += u;
+        }
+        warp_sums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t r = warp_sums[threadIdx.x >> 5] + incl - v;
+    __syncthreads();   // warp_sums is free again
+    return r;
+}
+
+constexpr int SELECT_HIST_BITS = 11;   // rank-prefix histogram over the top key bits: sign, exponent, two mantissa bits
+
+// BY_CELLS picks the form of the rounds; a launch of one form leaves the frames of the other alone (the candidate counts live
+// on the device, so the host launches both forms whenever the capacity admits the per-cell one).
+template <bool BY_CELLS>
+__global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_kernel(const SelectArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int frame = blockIdx.x;
     const int d = p.min_distance;
     const int pitch = p.cells_x + 2;                  // one-cell empty border all round
     const int n_cells = pitch * (p.cells_y + 2);
-    // per-cell state, shared (or, for very fine grids, global): best live key posted this round, and the kept point
-    unsigned long long *cmin;
-    uint32_t *cells;
-    if (p.cells_in_smem) {
-        cmin = reinterpret_cast<unsigned long long *>(smem);
-        cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
-    } else {
-        cmin = reinterpret_cast<unsigned long long *>(p.cell_scratch + int64_t(frame) * ((n_cells * 3 + 1) & ~1));  // keeps 8-byte alignment
-        cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
-    }
-    __shared__ uint32_t s_kept, s_count[2], s_admit;
+    // per-cell state, shared (or, for very fine grids, global): the best live key of the cell's candidates, the point kept in
+    // the cell, where the cell's candidates start in the binned list, and the round in which the cell's point was kept
+    uint8_t *cell_base = p.cells_in_smem ? smem : reinterpret_cast<uint8_t *>(p.cell_scratch) + int64_t(frame) * p.cell_stride;
+    unsigned long long *cmin = reinterpret_cast<unsigned long long *>(cell_base);
+    uint32_t *cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
+    uint32_t *cstart = cells + n_cells;                                 // n_cells + 1 entries
+    uint16_t *knew = reinterpret_cast<uint16_t *>(cstart + n_cells + 1);
+    __shared__ uint32_t s_kept, s_count, s_count2[2], s_admit, s_work, s_warp[32];
     __shared__ uint64_t s_limit;
-    // s_sort doubles as the 4096-bin (16 KiB) histogram of the rank-prefix search below
-    __shared__ uint64_t s_sort[SELECT_SORT_SMEM > 2048 ? SELECT_SORT_SMEM : 2048];
+    // s_sort doubles as the 2048-bin (8 KiB) histogram of the rank-prefix search below
+    __shared__ uint64_t s_sort[SELECT_SORT_SMEM];
     uint32_t *hist = reinterpret_cast<uint32_t *>(s_sort);
+    static_assert(SELECT_SORT_SMEM * 8 >= (4 << SELECT_HIST_BITS), "histogram must fit the sort buffer");
 
     const uint32_t count = p.cand_counts[frame];
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
+    if ((n > p.cells_min) != BY_CELLS) return;
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
-    // two key lists (live candidates of the current / next round), ping-pong: rounds read their candidates with one
-    // coalesced load instead of an index and a gather
-    uint64_t *list_a = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
-    uint64_t *list_b = list_a + p.cand_capacity;
+    // binned: the admitted candidates grouped by cell; admitted: the same keys in arrival order, before grouping
+    uint64_t *binned = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
+    uint64_t *admitted_keys = binned + p.cand_capacity;
+    // during the rounds the same storage lists the cells that must rescan their candidates (never more cells than candidates)
+    uint32_t *work = reinterpret_cast<uint32_t *>(admitted_keys);
     uint64_t *kept = p.kept_keys + int64_t(frame) * p.kept_capacity;
     const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536
     const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
     const uint32_t *mb = p.mask.bits ? p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row : nullptr;
+    auto cell_of = [&](uint32_t xy) {
+        const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
+        return (cy + 1) * pitch + cx + 1;
+    };
 
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
         cells[i] = kEmptyCell;
         cmin[i] = kDeadKey;
+        knew[i] = 0;
     }
-    if (threadIdx.x == 0) {
-        s_kept = 0u;
-        s_count[0] = 0u;
-        s_count[1] = 0u;
-    }
+    if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
 
     if (d < 0) {
@@ -192,41 +224,50 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
         if (threadIdx.x == 0) s_kept = min(n, uint32_t(p.kept_capacity));
         __syncthreads();
     } else {
-        // Each round: (1) every live candidate that a point kept in the previous round covers dies (a kept point covers
-        // itself); the others post their key to their cell (64-bit atomicMin) and move to the next round's list;
-        // (2) a candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no live
-        // better-ranked candidate within d, so the sequential walk would keep it: it is kept now.
+        // Admitted candidates are grouped by cell once (count, scan, scatter); after that a round costs work per CELL, not
+        // per live candidate:
+        //   (1) a cell whose best live candidate beats the best live candidates of the 8 cells around it keeps that candidate:
+        //       no live better-ranked candidate lies within d of it, so the sequential walk would keep it too;
+        //   (2) every cell next to a cell that kept a point this round drops its candidates within d of that point (a kept
+        //       point covers itself) and recomputes its best live candidate.
         // Only the best-ranked `want` kept points are returned, and a candidate's fate depends on better-ranked candidates
         // only, so the walk may stop at any rank prefix that already yields `want` kept points.  With many candidates the
-        // rounds therefore run on rank ranges: first the keys up to the histogram bin (top 12 key bits) that holds the K-th
+        // rounds therefore run on rank ranges: first the keys up to the histogram bin (top 11 key bits) that holds the K-th
         // best key; if that keeps too few, the next range (K fourfold) is admitted against the points kept so far.  Exact,
         // and a 4K Harris frame with 5 x 10^5 candidates and needed = 200 touches a few thousand of them.
         uint32_t want_kept = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;
         want_kept = min(want_kept, uint32_t(p.kp_capacity));
         const bool by_prefix = n > SELECT_PREFIX_MIN;
+        // Two forms of the rounds, same result.  Up to SELECT_CELLS_MIN candidates: work per round proportional to the
+        // candidates still alive (the first round kills most of them).  Beyond that -- FAST at the reference's default
+        // threshold makes every pixel a candidate, and its raster-ordered ranking needs hundreds of rounds -- the admitted
+        // candidates are grouped by cell once and a round costs work per CELL.
         uint32_t prefix_k = by_prefix ? max(uint32_t(SELECT_PREFIX_MIN / 2), 8u * want_kept) : n;
-        if (by_prefix) {   // histogram of the top 12 key bits, once
-            for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0u;
+        constexpr int BINS = 1 << SELECT_HIST_BITS;
+        if (by_prefix) {   // histogram of the top key bits, once
+            for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0u;
             __syncthreads();
             // neighbouring candidates mostly share a bin (FAST at a low threshold: 3 x 10^5 keys in a dozen bins), so each warp
             // first groups its lanes by bin and the group leader adds the group's size
             const uint32_t n_warp_rounded = (n + 31u) & ~31u;
             for (uint32_t i = threadIdx.x; i < n_warp_rounded; i += blockDim.x) {
-                const uint32_t bin = (i < n) ? uint32_t(__ldg(keys + i) >> 52) : 0xFFFFFFFFu;
+                const uint32_t bin = (i < n) ? uint32_t(__ldg(keys + i) >> (64 - SELECT_HIST_BITS)) : 0xFFFFFFFFu;
                 const uint32_t peers = __match_any_sync(0xffffffffu, bin);
                 if (bin != 0xFFFFFFFFu && lane_id() == __ffs(peers) - 1) atomicAdd(hist + bin, uint32_t(__popc(peers)));
             }
             __syncthreads();
         }
         uint64_t lower = 0ull;   // keys below this were admitted by earlier batches
+        uint32_t stamp = 0u;     // round counter behind knew[]
         for (int batch = 0;; ++batch) {
             uint64_t limit = kDeadKey;   // this batch admits lower <= key < limit
             uint32_t admitted = n;       // candidates with key < limit
             if (by_prefix && prefix_k < n) {
-                if (threadIdx.x < 32) {   // first bin at which the running count reaches prefix_k (one warp, 128 bins per lane)
+                if (threadIdx.x < 32) {   // first bin at which the running count reaches prefix_k (one warp, BINS / 32 bins per lane)
+                    constexpr int PER = BINS / 32;
                     uint32_t mine = 0u;
 #pragma unroll 4
-                    for (int b = 0; b < 128; ++b) mine += hist[threadIdx.x * 128 + b];
+                    for (int b = 0; b < PER; ++b) mine += hist[threadIdx.x * PER + b];
                     uint32_t incl = mine;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -238,13 +279,13 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
                         uint32_t run = before;
                         int b = 0;
 #pragma unroll 1
-                        for (; b < 128; ++b) {
-                            run += hist[threadIdx.x * 128 + b];
+                        for (; b < PER; ++b) {
+                            run += hist[threadIdx.x * PER + b];
                             if (run >= prefix_k) break;
                         }
-                        const uint32_t bin = threadIdx.x * 128 + b;
-                        s_limit = (bin >= 4095u) ? kDeadKey : (uint64_t(bin + 1u) << 52);
-                        s_admit = (bin >= 4095u) ? n : run;
+                        const uint32_t bin = threadIdx.x * PER + b;
+                        s_limit = (bin >= uint32_t(BINS - 1)) ? kDeadKey : (uint64_t(bin + 1u) << (64 - SELECT_HIST_BITS));
+                        s_admit = (bin >= uint32_t(BINS - 1)) ? n : run;
                     }
                 }
                 __syncthreads();
@@ -253,60 +294,205 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const SelectArgs
                 __syncthreads();
             }
 
-            if (threadIdx.x == 0) {
-                s_count[0] = 0u;
-                s_count[1] = 0u;
-            }
-            __syncthreads();
-            uint32_t m = n;          // live candidates entering the round
-            const uint64_t *cur = keys;      // round 0 walks the candidate slot itself
-            for (int round = 0;; ++round) {
-                uint64_t *nxt = (round & 1) ? list_b : list_a;
-                uint32_t *nxt_count = &s_count[round & 1];
-                const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
-                for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
-                    bool live = i < m;
-                    uint64_t key = 0ull;
-                    int c = 0;
-                    if (live) {
-                        key = cur[i];
-                        const uint32_t xy = cand_key_xy(key);
-                        const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
-                        const int cx = int(__umulhi(uint32_t(x), cell_magic)), cy = int(__umulhi(uint32_t(y), cell_magic));
-                        c = (cy + 1) * pitch + cx + 1;
-                        if (round == 0) {
+            if constexpr (BY_CELLS) {
+                // ---- admit: keys of this rank range that are not masked out and not covered by what is already kept ----
+                for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) cstart[i] = 0u;
+                if (threadIdx.x == 0) s_count = 0u;
+                __syncthreads();
+                const bool everything = !by_prefix && mb == nullptr;   // one batch, nothing to filter: the candidate slot itself is the list
+                if (everything) {
+                    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(cstart + cell_of(cand_key_xy(__ldg(keys + i))), 1u);
+                } else {
+                    const uint32_t rounded = (n + 31u) & ~31u;   // whole warps enter list_push together
+                    for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
+                        bool live = i < n;
+                        uint64_t key = 0ull;
+                        if (live) {
+                            key = __ldg(keys + i);
                             live = key >= lower && key < limit;
-                            // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
-                            if (live && mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
-                            // later batches start against everything the better-ranked batches kept
-                            if (live && batch > 0) live = !near_kept(cells, pitch, c, x, y, d);
-                        } else {
-                            live = !near_kept(cells, pitch, c, x, y, d);
+                            if (live) {
+                                const uint32_t xy = cand_key_xy(key);
+                                const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
+                                const int c = cell_of(xy);
+                                // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
+                                if (mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
+                                // later batches start against everything the better-ranked batches kept
+                                if (live && batch > 0) live = !near_kept(cells, pitch, c, x, y, d);
+                                if (live) atomicAdd(cstart + c, 1u);
+                            }
                         }
-                        if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
-                    }
-                    list_push(live, key, nxt, nxt_count);
-                }
-                __syncthreads();
-                m = *nxt_count;
-                if (m == 0u) break;
-                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                    const uint64_t key = nxt[i];
-                    const uint32_t xy = cand_key_xy(key);
-                    const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
-                    const int c = (cy + 1) * pitch + cx + 1;
-                    if (uint64_t(cmin[c]) != key) continue;
-                    if (key < neighbour_min(cmin, pitch, c)) {
-                        const uint32_t slot = atomicAdd(&s_kept, 1u);
-                        if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                        cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
+                        list_push(live, key, admitted_keys, &s_count);
                     }
                 }
                 __syncthreads();
-                for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
-                if (threadIdx.x == 0) s_count[(round + 1) & 1] = 0u;
-                cur = nxt;
+                const uint32_t m = everything ? n : s_count;
+                const uint64_t *source = everything ? keys : admitted_keys;
+                if (m != 0u) {
+                    // ---- group by cell: exclusive scan of the per-cell counts, then scatter ----
+                    {
+                        const int n_tot = n_cells + 1;
+                        const int per = (n_tot + int(blockDim.x) - 1) / int(blockDim.x);
+                        const int b0 = min(int(threadIdx.x) * per, n_tot), b1 = min(b0 + per, n_tot);
+                        uint32_t sum = 0u;
+                        for (int b = b0; b < b1; ++b) sum += cstart[b];
+                        uint32_t run = block_exclusive_scan(sum, s_warp);
+                        for (int b = b0; b < b1; ++b) {
+                            const uint32_t v = cstart[b];
+                            cstart[b] = run;
+                            run += v;
+                        }
+                    }
+                    __syncthreads();
+                    // scatter: cstart[c] runs from the start of cell c to its end, i.e. to the start of cell c + 1, so afterwards
+                    // the candidates of cell c are binned[cstart[c - 1] .. cstart[c]) (cell 0 is a border cell and stays empty)
+                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                        const uint64_t key = source[i];
+                        const int c = cell_of(cand_key_xy(key));
+                        binned[atomicAdd(cstart + c, 1u)] = key;
+                        atomicMin(cmin + c, static_cast<unsigned long long>(key));
+                    }
+                    __syncthreads();
+
+                    // ---- rounds ----
+                    const int sub = lane_id() & 7, group = int(threadIdx.x >> 3), n_groups = int(blockDim.x >> 3);
+                    const uint32_t group_mask = 0xFFu << (lane_id() & 24);
+                    for (;;) {
+                        if (++stamp == 0xFFFFu) {   // the 16-bit round stamps are about to wrap: forget the old ones
+                            for (int i = threadIdx.x; i < n_cells; i += blockDim.x) knew[i] = 0;
+                            stamp = 1u;
+                            __syncthreads();
+                        }
+                        if (threadIdx.x == 0) s_work = 0u;
+                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+                            const uint64_t mine = cmin[c];
+                            if (mine == kDeadKey) continue;   // border cells and cells without live candidates
+                            if (mine < neighbour_min(cmin, pitch, c)) {
+                                const uint32_t slot = atomicAdd(&s_kept, 1u);
+                                if (slot < uint32_t(p.kept_capacity)) kept[slot] = mine;
+                                cells[c] = cand_key_xy(mine);
+                                knew[c] = uint16_t(stamp);
+                            }
+                        }
+                        __syncthreads();
+                        // cells with live candidates next to a point kept this round go on the work list
+                        bool alive = false;
+                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+                            if (cmin[c] == kDeadKey) continue;
+                            bool fresh = false;
+    #pragma unroll
+                            for (int k = 0; k < 9; ++k) fresh |= knew[c + (k / 3 - 1) * pitch + (k % 3 - 1)] == uint16_t(stamp);
+                            if (fresh) work[atomicAdd(&s_work, 1u)] = uint32_t(c);
+                            else alive = true;
+                        }
+                        __syncthreads();
+                        // eight lanes per listed cell: drop the candidates the fresh points cover, recompute the cell's best
+                        const int n_work = int(s_work);
+                        for (int w = group; w < n_work; w += n_groups) {
+                            const int c = int(work[w]);
+                            // the boxes of pixels the fresh points cover, as packed 16-bit bounds (0xFFFFFFFF: matches no pixel); up to
+                            // three fresh points -- nearly always one -- take the short path
+                            uint32_t lo0 = 0xFFFFFFFFu, hi0 = 0xFFFFFFFFu, lo1 = 0xFFFFFFFFu, hi1 = 0xFFFFFFFFu, lo2 = 0xFFFFFFFFu, hi2 = 0xFFFFFFFFu;
+                            int n_fresh = 0;
+    #pragma unroll
+                            for (int k = 0; k < 9; ++k) {
+                                const int nb = c + (k / 3 - 1) * pitch + (k % 3 - 1);
+                                if (knew[nb] == uint16_t(stamp)) {
+                                    const uint32_t q = cells[nb];
+                                    const int qx = int(q & 0xFFFFu), qy = int(q >> 16);
+                                    const uint32_t lo = (uint32_t(max(qy - d, 0)) << 16) | uint32_t(max(qx - d, 0));
+                                    const uint32_t hi = (uint32_t(min(qy + d, 65534)) << 16) | uint32_t(min(qx + d, 65534));
+                                    if (n_fresh == 0) lo0 = lo, hi0 = hi;
+                                    else if (n_fresh == 1) lo1 = lo, hi1 = hi;
+                                    else if (n_fresh == 2) lo2 = lo, hi2 = hi;
+                                    ++n_fresh;
+                                }
+                            }
+                            const uint32_t js = cstart[c - 1] + sub, je = cstart[c];
+                            uint64_t best = kDeadKey;
+                            if (n_fresh <= 3) {
+                                for (uint32_t j = js; j < je; j += 8) {
+                                    const uint64_t key = binned[j];
+                                    const uint32_t xy = cand_key_xy(key);   // dropped candidates read 0xFFFFFFFF, outside every box
+                                    const bool hit = (__vminu2(__vmaxu2(xy, lo0), hi0) == xy) | (__vminu2(__vmaxu2(xy, lo1), hi1) == xy) |
+                                                     (__vminu2(__vmaxu2(xy, lo2), hi2) == xy);
+                                    if (hit) binned[j] = kDeadKey;
+                                    else best = min(best, key);
+                                }
+                            } else {
+                                for (uint32_t j = js; j < je; j += 8) {
+                                    const uint64_t key = binned[j];
+                                    const uint32_t xy = cand_key_xy(key);
+                                    const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
+                                    if (key != kDeadKey && near_kept(cells, pitch, c, x, y, d)) binned[j] = kDeadKey;   // every kept point, fresh or not
+                                    else best = min(best, key);
+                                }
+                            }
+    #pragma unroll
+                            for (int o = 1; o < 8; o <<= 1) best = min(best, __shfl_xor_sync(group_mask, best, o));
+                            if (sub == 0) cmin[c] = best;
+                            alive |= best != kDeadKey;
+                        }
+                        if (!__syncthreads_or(alive)) break;
+                    }
+                }
+            } else {
+                // ---- candidate-centric rounds ----
+                // (1) every live candidate that a point kept in the previous round covers dies (a kept point covers itself);
+                //     the others post their key to their cell (64-bit atomicMin) and move to the next round's list;
+                // (2) a candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells is kept.
+                uint64_t *list_a = binned, *list_b = admitted_keys;
+                if (threadIdx.x == 0) {
+                    s_count2[0] = 0u;
+                    s_count2[1] = 0u;
+                }
                 __syncthreads();
+                uint32_t m = n;               // live candidates entering the round
+                const uint64_t *cur = keys;   // round 0 walks the candidate slot itself
+                for (int round = 0;; ++round) {
+                    uint64_t *nxt = (round & 1) ? list_b : list_a;
+                    uint32_t *nxt_count = &s_count2[round & 1];
+                    const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
+                    for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
+                        bool live = i < m;
+                        uint64_t key = 0ull;
+                        if (live) {
+                            key = cur[i];
+                            const uint32_t xy = cand_key_xy(key);
+                            const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
+                            const int c = cell_of(xy);
+                            if (round == 0) {
+                                live = key >= lower && key < limit;
+                                // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
+                                if (live && mb != nullptr) live = (mb[int64_t(y) * p.mask.words_per_row + (x >> 5)] >> (x & 31)) & 1u;
+                                // later batches start against everything the better-ranked batches kept
+                                if (live && batch > 0) live = !near_kept(cells, pitch, c, x, y, d);
+                            } else {
+                                live = !near_kept(cells, pitch, c, x, y, d);
+                            }
+                            if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
+                        }
+                        list_push(live, key, nxt, nxt_count);
+                    }
+                    __syncthreads();
+                    m = *nxt_count;
+                    if (m == 0u) break;
+                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                        const uint64_t key = nxt[i];
+                        const uint32_t xy = cand_key_xy(key);
+                        const int c = cell_of(xy);
+                        if (uint64_t(cmin[c]) != key) continue;
+                        if (key < neighbour_min(cmin, pitch, c)) {
+                            const uint32_t slot = atomicAdd(&s_kept, 1u);
+                            if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
+                            cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
+                        }
+                    }
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
+                    if (threadIdx.x == 0) s_count2[(round + 1) & 1] = 0u;
+                    cur = nxt;
+                    __syncthreads();
+                }
             }
             // enough kept points (or every candidate admitted): done.  Otherwise admit the next, four times larger, rank range;
             // what has been kept so far stays kept (those decisions never depend on worse-ranked candidates).
@@ -354,13 +540,24 @@ cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t 
     return cudaGetLastError();
 }
 
-size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? size_t(a.cells_x + 2) * (a.cells_y + 2) * 12 : 0; }
+size_t select_cell_bytes(int cells_x, int cells_y) {   // cmin (8) + kept point (4) + list start (4, one extra entry) + round stamp (2) per cell
+    const size_t n = size_t(cells_x + 2) * (cells_y + 2);
+    return (n * 18 + 4 + 15) & ~size_t(15);
+}
+
+size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_cell_bytes(a.cells_x, a.cells_y) : 0; }
 
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(args);
-    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const int threads = args.cells_in_smem ? SELECT_THREADS : SELECT_MAX_THREADS;
+    cudaError_t e = cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    select_kernel<<<args.n_frames, SELECT_THREADS, smem, stream>>>(args);
+    select_kernel<false><<<args.n_frames, threads, smem, stream>>>(args);
+    if (args.cand_capacity > args.cells_min) {   // some frame may hold enough candidates for the per-cell form
+        e = cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        select_kernel<true><<<args.n_frames, threads, smem, stream>>>(args);
+    }
     return cudaGetLastError();
 }
 

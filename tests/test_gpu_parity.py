@@ -468,6 +468,62 @@ def test_fast_sparse_equals_dense_other_diffs_and_batches(ctx, dense_ctx, fast_n
             assert np.array_equal(cnt_a, cnt_b) and np.array_equal(kp_a, kp_b)
 
 
+# ---- the two forms of the selection rounds (fd_select.cu): per live candidate and per cell -------------------------------
+def _ctx_with_select_threshold(value):
+    import os
+    os.environ["FD_B200_SELECT_CELLS_MIN"] = str(value)
+    try:
+        return fd.Context(0)
+    finally:
+        del os.environ["FD_B200_SELECT_CELLS_MIN"]
+
+
+def test_selection_per_cell_equals_per_candidate(checker):
+    """Frames below the switch-over count are selected per candidate, frames above it per cell; forcing either form on the
+    same candidates must give the same keypoints, with and without pre-existing features, for one and for several rank
+    batches, fine and coarse cell grids."""
+    from feature_detector_b200.synth import synth
+    per_cell, per_cand = _ctx_with_select_threshold(0), _ctx_with_select_threshold(1 << 30)
+    try:
+        rng = np.random.default_rng(11)
+        batches = [np.stack([synth(320, 200, i) for i in range(6)]),
+                   rng.integers(0, 256, (3, 120, 200), dtype=np.uint8),
+                   np.stack([synth(752, 480, 70 + i) for i in range(2)])]
+        cases = [(fd.HARRIS, 0.1, 15, 200, 12), (fd.HARRIS, 30.0, 3, 5000, 12), (fd.SHI_TOMAS, 0.1, 40, 1000, 12), (fd.FAST, 0.1, 15, 200, 12),
+                 (fd.FAST, 10.0, 20, 200, 9), (fd.FAST, 0.1, 0, 300, 9), (fd.HARRIS, 0.1, 1, 100000, 12), (fd.FAST, 0.1, 7, 0, 12)]
+        for frames in batches:
+            h, w = frames.shape[1:]
+            existing = [np.stack([rng.integers(0, w, 9), rng.integers(0, h, 9)], 1).astype(np.float32) for _ in range(len(frames))]
+            for kind, thr, d, n, fast_n in cases:
+                for with_existing in (False, True):
+                    out = []
+                    for c in (per_cell, per_cand):
+                        c.upload(frames)
+                        if with_existing:
+                            c.set_existing_features(existing)
+                        else:
+                            c.set_existing_features([])
+                        c.detect(fd.DetectParams(kind, thr, d, n, fast_n=fast_n), 0)
+                        kp, cnt = c.keypoints(max(n, 1))
+                        out.append((kp, cnt))
+                    assert np.array_equal(out[0][1], out[1][1]), (kind, thr, d, n, with_existing)
+                    for f in range(len(frames)):
+                        k = out[0][1][f]
+                        assert np.array_equal(out[0][0][f, :k], out[1][0][f, :k]), (kind, thr, d, n, with_existing, f)
+            # and against the checker for one case per batch (ties are open in the reference's unstable sort)
+            per_cell.upload(frames)
+            per_cell.set_existing_features([])
+            per_cell.detect(fd.DetectParams(fd.FAST, 0.1, 15, 200, fast_n=12), 0)
+            kp, cnt = per_cell.keypoints(200)
+            for f in range(len(frames)):
+                o = checker.detect(FAST, frames[f], 0.1, 15, 200, fast_n=12)
+                feats = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
+                assert np.array_equal(feats, o["features"]), f
+    finally:
+        per_cell.close()
+        per_cand.close()
+
+
 def test_host_pipeline_equals_single_call(ctx, torch_cuda):
     """Chunked, double-buffered host batches (pipeline.HostPipeline) give what one fd_detect over the batch gives."""
     from feature_detector_b200.pipeline import HostPipeline
