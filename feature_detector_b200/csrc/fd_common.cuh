@@ -92,6 +92,45 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t *counter, uint32_t n_m
     }
     return base + incl - n_mine;
 }
+// Ascending bitonic network over keys[0, n) (n need not be a power of two): ascending-only comparators, so the
+// tail beyond n acts as +inf padding.
+__device__ inline void block_bitonic_sort(uint64_t *keys, uint32_t n) {
+    if (n < 2) return;
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t i = threadIdx.x; i < np2 / 2; i += blockDim.x) {  // mirror stage
+            const uint32_t off = i & (hk - 1);
+            const uint32_t lo = ((i - off) << 1) + off;
+            const uint32_t hi = ((i - off) << 1) + (k - 1 - off);
+            if (hi < n) {
+                const uint64_t a = keys[lo], b = keys[hi];
+                if (a > b) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                const uint32_t off = i & (j - 1);
+                const uint32_t lo = ((i - off) << 1) + off;
+                const uint32_t hi = lo + j;
+                if (hi < n) {
+                    const uint64_t a = keys[lo], b = keys[hi];
+                    if (a > b) {
+                        keys[lo] = b;
+                        keys[hi] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace fdb

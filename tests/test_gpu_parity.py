@@ -305,6 +305,27 @@ def test_lsd_norm_every_gradient_pair(ctx, checker):
     assert worst <= 1e-6, worst   # budget 1e-5 (BASELINE.json north_star); the kernel's arctangent is good to 5e-7
 
 
+def test_lsd_seed_order_of_a_ramp(ctx, checker):
+    """A linear ramp gives every pixel the same gradient: one magnitude bucket holds (nearly) all seeds, which takes the
+    in-place sort of the ordering kernel instead of its shared-memory tiles."""
+    r, c = np.mgrid[0:300, 0:420]
+    img = ((5 * r + 3 * c) & 0xFF).astype(np.uint8)
+    h, w = img.shape
+    ctx.upload(img)
+    ctx.lsd_field(fd.LsdParams(2.0, 1))
+    g = ctx.lsd_download(0)
+    o = checker.lsd_map(img, 2.0)
+    norm = g["norm"][:h - 1, :w - 1]
+    assert np.array_equal(norm.view(np.uint32), o["norm"].view(np.uint32))
+    assert g["n_valid"] == int(o["valid"].sum()) > 100000
+    rows_, cols_ = g["sorted_idx"] // w, g["sorted_idx"] % w
+    seq = norm[rows_, cols_]
+    assert np.array_equal(seq, o["norm"][o["sorted_rc"][:, 0], o["sorted_rc"][:, 1]])
+    cm = cols_.astype(np.int64) * h + rows_
+    assert np.all(np.diff(cm)[np.diff(seq) == 0] > 0)          # ties in the reference's push order: column outer, row inner
+    assert len(np.unique(g["sorted_idx"])) == len(g["sorted_idx"])
+
+
 def test_bound_device_frames_with_pitch(ctx, checker, torch_cuda):
     """Frames that already live on the device, including an unaligned pitch (re-pitched internally)."""
     from feature_detector_b200.synth import synth_batch
