@@ -12,20 +12,24 @@
 //
 // select_kernel: one CTA per frame, no global sort.  Frame pixels are binned into a grid of (d+1)-sided
 // cells; two kept points can never share a cell, and anything within d of a pixel lies in the 3x3 cells
-// around it.  Rounds until no candidate is alive:
-//   A  every live candidate within d of a point kept in the previous round dies; the others post their key
-//      to their cell with a shared-memory atomicMin (two 32-bit phases: response word, then position word);
-//   B  a live candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no
-//      live better-ranked candidate within d, so the sequential walk would keep it: it is kept now, written
-//      to the frame's kept list and to the cell grid.  All such candidates of a round are independent.
+// around it.  Rounds until no candidate is alive, in one of two forms with identical results:
+//   per candidate (select_kernel<false>, frames of up to SELECT_CELLS_MIN candidates)
+//     A  every live candidate within d of a point kept in the previous round dies; the others post their key
+//        to their cell with a shared-memory 64-bit atomicMin and move to the next round's key list;
+//     B  a live candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no
+//        live better-ranked candidate within d, so the sequential walk would keep it: it is kept now, written
+//        to the frame's kept list and to the cell grid.  All such candidates of a round are independent.
+//     Work per round is proportional to the candidates still alive, and the first round kills most of them.
+//   per cell (select_kernel<true>, frames with more candidates: FAST at the reference's default threshold, 4K Harris)
+//     the admitted candidates are grouped by cell once; a cell whose best live candidate beats the best of the 8 cells
+//     around it keeps it; cells next to a fresh point drop the candidates it covers and recompute their best.
 // The kept list is then sorted by key (a few hundred entries, bitonic in shared memory) and cut at
 // max(needed - existing, 1) -- the reference tests the count AFTER each push (:67-68), so needed = 0 still
-// yields one feature.  Work per round is proportional to the candidates still alive, and the first round kills
-// most of them.  Pre-existing features need no handling here: their squares were already masked out of
+// yields one feature.  Pre-existing features need no handling here: their squares were already masked out of
 // candidate generation with the same d (feature_point_detector.cpp:12-16); they only count toward `needed`.
 //
-// sort_kernel: bitonic sort of each frame's keys (shared memory when they fit).  Not on the detection path any
-// more; used for the LSD seed order and when the caller asks for the sorted candidate list on the device.
+// sort_kernel: bitonic sort of each frame's keys (shared memory when they fit).  Not on the detection path;
+// used when the caller asks for the sorted candidate list on the device.
 #include "fd_kernels.cuh"
 
 namespace fdb {

@@ -8,7 +8,10 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if 'Source' in r][0]
 hdr = rows[hi]; col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hi + 1:]:   # first captured launch only (each launch has its own table)
+    if r == hdr: break
+    if len(r) == len(hdr): data.append(r)
 tot = sum(int(r[col['Instructions Executed']]) for r in data)
 print('total warp-instructions', tot, 'static', len(data))
 run, runs = None, []
