@@ -111,6 +111,36 @@ public:
     const T &y() const { return data()[1]; }
 
     void setZero() { std::fill(data(), data() + size(), T(0)); }
+    void setConstant(const T &v) { std::fill(data(), data() + size(), v); }
+    static Matrix Ones(int r, int c) {
+        Matrix m;
+        m.setConstant(r, c, T(1));
+        return m;
+    }
+    // Rectangular views that can only be cleared: all the reference does with block / topRows / ... (nn_feature_point_detector.cpp:64-83).
+    class BlockView {
+    public:
+        BlockView(Matrix &m, int r0, int c0, int h, int w): m_(m), r0_(r0), c0_(c0), h_(h), w_(w) {}
+        void setZero() {
+            for (int r = r0_; r < r0_ + h_; ++r)
+                for (int c = c0_; c < c0_ + w_; ++c) m_(r, c) = T(0);
+        }
+    private:
+        Matrix &m_;
+        int r0_, c0_, h_, w_;
+    };
+    BlockView block(int r0, int c0, int h, int w) { return BlockView(*this, r0, c0, h, w); }
+    BlockView topRows(int n) { return BlockView(*this, 0, 0, n, cols()); }
+    BlockView bottomRows(int n) { return BlockView(*this, rows() - n, 0, n, cols()); }
+    BlockView leftCols(int n) { return BlockView(*this, 0, 0, rows(), n); }
+    BlockView rightCols(int n) { return BlockView(*this, 0, cols() - n, rows(), n); }
+    template <typename U>
+    Matrix<U, R, C, Order> cast() const {
+        Matrix<U, R, C, Order> out;
+        if constexpr (kDyn) out.resize(rows(), cols());
+        for (int64_t i = 0; i < size(); ++i) out.data()[i] = static_cast<U>(data()[i]);
+        return out;
+    }
     void setZero(int r, int c) {
         resize(r, c);
         setZero();
@@ -178,6 +208,48 @@ private:
     Buf buf_;
     int rows_ = (R == Dynamic ? 0 : R);
     int cols_ = (C == Dynamic ? (R == Dynamic ? 0 : 1) : C);
+};
+
+// One row of a mapped matrix, as values: .cast<U>() and .transpose() keep the values, and the result converts to / assigns
+// into a column vector of the same length (nn_feature_point_detector.cpp:214,225).
+template <typename T>
+class RowValues {
+public:
+    explicit RowValues(std::vector<T> v): v_(std::move(v)) {}
+    template <typename U>
+    RowValues<U> cast() const {
+        std::vector<U> out(v_.size());
+        for (size_t i = 0; i < v_.size(); ++i) out[i] = static_cast<U>(v_[i]);
+        return RowValues<U>(std::move(out));
+    }
+    const RowValues &transpose() const { return *this; }
+    template <int N, int O>
+    operator Matrix<T, N, 1, O>() const {
+        Matrix<T, N, 1, O> out;
+        if constexpr (N == Dynamic) out.resize(int(v_.size()), 1);
+        for (int i = 0; i < int(v_.size()) && i < int(out.size()); ++i) out[i] = v_[i];
+        return out;
+    }
+private:
+    std::vector<T> v_;
+};
+
+// Read-only view of a row-major buffer with the shape of PlainType.
+template <typename PlainType>
+class Map;
+template <typename T, int R, int C, int Order>
+class Map<const Matrix<T, R, C, Order>> {
+    static_assert(Order == RowMajor, "only row-major maps are used (MatImgF, TMatImg<int64_t>)");
+public:
+    Map(const T *data, int rows, int cols): data_(data), rows_(rows), cols_(cols) {}
+    int rows() const { return rows_; }
+    int cols() const { return cols_; }
+    const T *data() const { return data_; }
+    const T &operator()(int r, int c) const { return data_[int64_t(r) * cols_ + c]; }
+    RowValues<T> row(int r) const { return RowValues<T>(std::vector<T>(data_ + int64_t(r) * cols_, data_ + int64_t(r + 1) * cols_)); }
+private:
+    const T *data_;
+    int rows_, cols_;
 };
 
 // 2x2 * 2x1: coefficient i = m(i,0)*v0 + m(i,1)*v1 (Eigen's lazy coefficient product order).

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 __all__ = ["Context", "FdError", "HARRIS", "SHI_TOMAS", "FAST", "SAMPLE_BILINEAR", "SAMPLE_TRUNCATE", "library_path", "load_library",
-           "DetectParams", "BriefParams", "LsdParams", "sparsify"]
+           "DetectParams", "BriefParams", "LsdParams", "NnParams", "sparsify"]
 
 HARRIS, SHI_TOMAS, FAST = 0, 1, 2
 SAMPLE_BILINEAR, SAMPLE_TRUNCATE = 0, 1
@@ -57,6 +57,15 @@ class LsdParams(C.Structure):
 
     def __init__(self, min_valid_gradient_norm=20.0, want_sorted=1):
         super().__init__(min_valid_gradient_norm, want_sorted)
+
+
+class NnParams(C.Structure):
+    """NNFeaturePointDetector::Options fields the post-processing reads (nn_feature_point_detector.h:22-31)."""
+    _fields_ = [("min_response", C.c_float), ("invalid_boundary", C.c_int32), ("min_feature_distance", C.c_int32), ("max_features", C.c_uint32),
+                ("reserved", C.c_int32)]
+
+    def __init__(self, min_response=0.1, invalid_boundary=3, min_feature_distance=15, max_features=240):
+        super().__init__(min_response, invalid_boundary, min_feature_distance, max_features, 0)
 
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("reserved", "<i4")])
@@ -107,6 +116,9 @@ def load_library():
         "fd_download_descriptors": (C.c_int, [vp, vp, C.c_int]),
         "fd_device_descriptors": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int)]),
         "fd_lsd_field": (C.c_int, [vp, C.POINTER(LsdParams), vp, vp, vp, vp]),
+        "fd_nn_select_from_heatmap": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(NnParams), C.c_int]),
+        "fd_nn_sample_descriptors": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+        "fd_nn_download_descriptors": (C.c_int, [vp, vp, C.c_int]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
         "fd_debug_fast_offset_bits": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), i32p]),
@@ -308,6 +320,22 @@ class Context:
         """Like descriptors(), into a caller-owned (n_frames, capacity, 32) uint8 array."""
         assert desc.dtype == np.uint8 and desc.flags.c_contiguous and desc.shape[0] == self.n_frames and desc.shape[2] == 32
         self._ck(self._lib.fd_download_descriptors(self._h, desc.ctypes.data_as(C.c_void_p), desc.shape[1]))
+
+    # -- NN detector post-processing ---------------------------------------------------------------------
+    def nn_select(self, dev_heatmap: int, rows: int, cols: int, n_frames: int, params: NnParams, cand_capacity: int = 0):
+        """Heat maps (device pointer, n_frames x rows x cols float32) -> keypoints (fetch with keypoints())."""
+        self._ck(self._lib.fd_nn_select_from_heatmap(self._h, C.c_void_p(dev_heatmap), rows, cols, n_frames, C.byref(params), cand_capacity))
+        self.rows, self.cols, self.n_frames = rows, cols, n_frames
+
+    def nn_sample_descriptors(self, dev_maps: int, channels: int, map_rows: int, map_cols: int, dev_out: int = 0):
+        self._ck(self._lib.fd_nn_sample_descriptors(self._h, C.c_void_p(dev_maps), channels, map_rows, map_cols, C.c_void_p(dev_out or 0)))
+        self._nn_channels = channels
+
+    def nn_descriptors(self, kp_capacity: int):
+        """(n_frames, kp_capacity, channels) float32 from the context-owned buffer."""
+        d = np.zeros((self.n_frames, kp_capacity, self._nn_channels), np.float32)
+        self._ck(self._lib.fd_nn_download_descriptors(self._h, d.ctypes.data_as(C.c_void_p), kp_capacity))
+        return d
 
     # -- LSD -----------------------------------------------------------------------------------------
     def lsd_field(self, params: LsdParams, dev_norm: int = 0, dev_angle: int = 0, dev_sorted: int = 0, dev_n_valid: int = 0):

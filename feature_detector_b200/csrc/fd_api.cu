@@ -74,6 +74,9 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
+    DevBuf nn_desc;
+    int nn_channels = 0;
+    bool have_nn_desc = false;
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed, lsd_item_counts, lsd_chunk_sum;
     size_t lsd_hist_zeroed = 0;   // bytes of lsd_hist known to be zero (the scatter kernel restores the zeros it consumes)
     float *lsd_norm_p = nullptr, *lsd_angle_p = nullptr;
@@ -449,7 +452,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
 // Greedy selection over candidate keys of n_frames frames of rows x cols pixels (the context's own candidates, or keys
 // gathered from the row tiles of one frame).
 fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int cols, int n_frames, uint64_t *keys, const uint32_t *counts,
-                     uint32_t capacity) {
+                     uint32_t capacity, uint32_t xy_xor = 0u) {
     struct { int rows, cols, n_frames; } fv = {rows, cols, n_frames};
     const int kp_cap = int(std::max<uint32_t>(1u, std::min<uint32_t>(p->needed_feature_num, 1u << 20)));
     ctx->kp_capacity = kp_cap;
@@ -487,6 +490,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.kept_keys = static_cast<uint64_t *>(ctx->kept.ptr);
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;
+    a.xy_xor = xy_xor;
     FD_CUDA(ctx, launch_select(a, ctx->stream));
     ctx->launches += (a.cand_capacity > a.cells_min) ? 2 : 1;   // the per-cell form is launched only when the capacity admits it
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
@@ -539,7 +543,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -869,6 +873,105 @@ fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *
     if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
     if (dev_desc) *dev_desc = static_cast<const uint8_t *>(ctx->desc.ptr);
     if (kp_capacity) *kp_capacity = ctx->desc_capacity;
+    return FD_OK;
+}
+
+// ---- NN detector post-processing (nn_feature_point_detector.cpp:59-72, 128-155, 163-193) ------------------------------
+fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, int rows, int cols, int n_frames, const fd_nn_params *params,
+                                    int cand_capacity) {
+    if (!ctx || !dev_heatmap || !params || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_nn_select_from_heatmap: bad argument");
+    if (params->reserved != 0 || params->invalid_boundary < 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_nn_params: invalid_boundary must be >= 0 and reserved 0");
+    if (rows > 65535 || cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "maps are limited to 65535 x 65535");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t px = int64_t(rows) * cols;
+    const uint32_t cap = cand_capacity > 0 ? uint32_t(std::min<int64_t>(cand_capacity, px)) : uint32_t(px);
+    ctx->cand_capacity = cap;
+    FD_TRY(reserve(ctx, ctx->keys, size_t(n_frames) * cap * 8));
+    FD_TRY(reserve(ctx, ctx->counts, size_t(n_frames) * 4));
+    FD_TRY(reserve(ctx, ctx->flags, 16));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->counts.ptr, 0, size_t(n_frames) * 4, ctx->stream));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->flags.ptr, 0, 16, ctx->stream));
+    ctx->have_candidates = ctx->have_keypoints = ctx->have_nn_desc = false;
+    ctx->candidates_sorted = false;
+
+    // pre-existing features clear their squares from the mask (CreateMask -> UpdateMaskByFeatures, .cpp:68-70, 85-91)
+    MaskView mask = {};
+    if (ctx->have_existing) {
+        if (ctx->existing_frames != n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "existing features were set for a different number of frames");
+        const int wpr = (cols + 31) / 32 + 1;
+        FD_TRY(reserve(ctx, ctx->mask_bits, size_t(n_frames) * rows * wpr * 4));
+        MaskArgs m = {};
+        m.rows = rows;
+        m.cols = cols;
+        m.n_frames = n_frames;
+        m.min_distance = params->min_feature_distance;
+        m.xy = static_cast<const float *>(ctx->existing_xy.ptr);
+        m.counts = static_cast<const int32_t *>(ctx->existing_counts.ptr);
+        m.capacity = ctx->existing_capacity;
+        m.bits = static_cast<uint32_t *>(ctx->mask_bits.ptr);
+        m.words_per_row = wpr;
+        FD_CUDA(ctx, launch_mask(m, ctx->stream));
+        ++ctx->launches;
+        mask.bits = m.bits;
+        mask.words_per_row = wpr;
+    }
+    ctx->mask_view = mask;
+
+    NnHeatmapArgs a = {};
+    a.heatmap = dev_heatmap;
+    a.rows = rows;
+    a.cols = cols;
+    a.n_frames = n_frames;
+    a.min_response = params->min_response;
+    a.invalid_boundary = params->invalid_boundary;
+    a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
+    a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
+    a.cand_capacity = cap;
+    FD_CUDA(ctx, launch_nn_heatmap(a, ctx->sm_count, ctx->stream));
+    ++ctx->launches;
+
+    fd_detect_params sel = {};
+    sel.kind = FD_HARRIS;   // selection only reads the distance and the count
+    sel.min_feature_distance = params->min_feature_distance;
+    sel.needed_feature_num = params->max_features;
+    ctx->select_frames = n_frames;
+    return run_select(ctx, &sel, rows, cols, n_frames, a.cand_keys, a.cand_counts, cap, 0xFFFFFFFFu);
+}
+
+fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, float *dev_out) {
+    if (!ctx || !dev_maps || channels <= 0 || map_rows <= 0 || map_cols <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_nn_sample_descriptors: bad argument");
+    if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "no keypoints selected");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nf = ctx->select_frames;
+    if (!dev_out) {
+        FD_TRY(reserve(ctx, ctx->nn_desc, size_t(nf) * ctx->kp_capacity * channels * 4));
+        dev_out = static_cast<float *>(ctx->nn_desc.ptr);
+    }
+    NnDescriptorArgs a = {};
+    a.maps = dev_maps;
+    a.channels = channels;
+    a.map_rows = map_rows;
+    a.map_cols = map_cols;
+    a.n_frames = nf;
+    a.keypoints = static_cast<const float4 *>(ctx->kp.ptr);
+    a.kp_counts = static_cast<const int32_t *>(ctx->kp_counts.ptr);
+    a.kp_capacity = ctx->kp_capacity;
+    a.out = dev_out;
+    FD_CUDA(ctx, launch_nn_descriptors(a, ctx->stream));
+    ++ctx->launches;
+    ctx->nn_channels = channels;
+    ctx->have_nn_desc = (dev_out == ctx->nn_desc.ptr);
+    return FD_OK;
+}
+
+fd_status fd_nn_download_descriptors(fd_context *ctx, float *host_desc, int kp_capacity) {
+    if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_nn_desc) return fail(ctx, FD_ERR_NOT_READY, "fd_nn_sample_descriptors has not written to the context's buffer");
+    const size_t row = size_t(ctx->nn_channels) * 4;
+    const int w = std::min(kp_capacity, ctx->kp_capacity);
+    FD_CUDA(ctx, cudaMemcpy2DAsync(host_desc, size_t(kp_capacity) * row, ctx->nn_desc.ptr, size_t(ctx->kp_capacity) * row, size_t(w) * row,
+                                   size_t(ctx->select_frames), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FD_OK;
 }
 

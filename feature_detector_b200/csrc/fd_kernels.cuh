@@ -1,6 +1,8 @@
 // Internal launch interface between the C-ABI layer (fd_api.cu) and the kernels.
 #pragma once
 
+#include <algorithm>
+
 #include "fd_common.cuh"
 
 namespace fdb {
@@ -126,6 +128,7 @@ struct SelectArgs {
     int cells_in_smem;
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
+    uint32_t xy_xor;                // 0, or 0xFFFFFFFF when the keys carry the complemented position (NN heat maps: among equal responses the later pixel first)
 };
 size_t select_cell_bytes(int cells_x, int cells_y);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
@@ -163,6 +166,27 @@ cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
 constexpr int LSD_SEED_ORDER_LAUNCHES = 4;
 size_t lsd_chunk_sum_bytes(int n_frames);
 cudaError_t launch_seed_order(const LsdArgs &args, uint64_t *bucketed, uint32_t *start, uint32_t *chunk_sum, int32_t *sorted_idx, cudaStream_t stream);
+
+// ---- NN detector post-processing (nn_feature_point_detector.cpp:59-72, 128-155, 163-193), fd_nn.cu --------------------
+struct NnHeatmapArgs {
+    const float *heatmap;      // n_frames * rows * cols, row-major, no pitch
+    int rows, cols, n_frames;
+    float min_response;        // kMinResponse
+    int invalid_boundary;      // kInvalidBoundary
+    uint64_t *cand_keys;       // high word ~ordered(response), low word ~((row << 16) | col): equal responses rank the later pixel first
+    uint32_t *cand_counts;
+    uint32_t cand_capacity;
+};
+cudaError_t launch_nn_heatmap(const NnHeatmapArgs &args, int sm_count, cudaStream_t stream);
+struct NnDescriptorArgs {
+    const float *maps;         // n_frames * channels planes of map_rows x map_cols floats
+    int channels, map_rows, map_cols, n_frames;
+    const float4 *keypoints;   // slots of kp_capacity per frame: (x, y, *, *)
+    const int32_t *kp_counts;
+    int kp_capacity;
+    float *out;                // channels floats per keypoint slot
+};
+cudaError_t launch_nn_descriptors(const NnDescriptorArgs &args, cudaStream_t stream);
 
 // ---- shared: segmented key sort (one CTA per segment) -------------------------------------------
 cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t slot, int n_segments, uint32_t capacity, uint32_t *overflow_flag,

@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536
     const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
     const uint32_t *mb = p.mask.bits ? p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row : nullptr;
+    const uint32_t xy_xor = p.xy_xor;
+    auto key_xy = [&](uint64_t key) { return uint32_t(key) ^ xy_xor; };   // (row << 16) | col
     auto cell_of = [&](uint32_t xy) {
         const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
         return (cy + 1) * pitch + cx + 1;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                 __syncthreads();
                 const bool everything = !by_prefix && mb == nullptr;   // one batch, nothing to filter: the candidate slot itself is the list
                 if (everything) {
-                    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(cstart + cell_of(cand_key_xy(__ldg(keys + i))), 1u);
+                    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(cstart + cell_of(key_xy(__ldg(keys + i))), 1u);
                 } else {
                     const uint32_t rounded = (n + 31u) & ~31u;   // whole warps enter list_push together
                     for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             key = __ldg(keys + i);
                             live = key >= lower && key < limit;
                             if (live) {
-                                const uint32_t xy = cand_key_xy(key);
+                                const uint32_t xy = key_xy(key);
                                 const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                                 const int c = cell_of(xy);
                                 // a candidate on a masked-out pixel is never accepted (feature_point_detector.cpp:66)
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     // the candidates of cell c are binned[cstart[c - 1] .. cstart[c]) (cell 0 is a border cell and stays empty)
                     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
                         const uint64_t key = source[i];
-                        const int c = cell_of(cand_key_xy(key));
+                        const int c = cell_of(key_xy(key));
                         binned[atomicAdd(cstart + c, 1u)] = key;
                         atomicMin(cmin + c, static_cast<unsigned long long>(key));
                     }
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             if (mine < neighbour_min(cmin, pitch, c)) {
                                 const uint32_t slot = atomicAdd(&s_kept, 1u);
                                 if (slot < uint32_t(p.kept_capacity)) kept[slot] = mine;
-                                cells[c] = cand_key_xy(mine);
+                                cells[c] = key_xy(mine);
                                 knew[c] = uint16_t(stamp);
                             }
                         }
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                         for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
                             if (cmin[c] == kDeadKey) continue;
                             bool fresh = false;
-    #pragma unroll
+#pragma unroll
                             for (int k = 0; k < 9; ++k) fresh |= knew[c + (k / 3 - 1) * pitch + (k % 3 - 1)] == uint16_t(stamp);
                             if (fresh) work[atomicAdd(&s_work, 1u)] = uint32_t(c);
                             else alive = true;
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             // three fresh points -- nearly always one -- take the short path
                             uint32_t lo0 = 0xFFFFFFFFu, hi0 = 0xFFFFFFFFu, lo1 = 0xFFFFFFFFu, hi1 = 0xFFFFFFFFu, lo2 = 0xFFFFFFFFu, hi2 = 0xFFFFFFFFu;
                             int n_fresh = 0;
-    #pragma unroll
+#pragma unroll
                             for (int k = 0; k < 9; ++k) {
                                 const int nb = c + (k / 3 - 1) * pitch + (k % 3 - 1);
                                 if (knew[nb] == uint16_t(stamp)) {
@@ -377,22 +379,22 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             if (n_fresh <= 3) {
                                 for (uint32_t j = js; j < je; j += 8) {
                                     const uint64_t key = binned[j];
-                                    const uint32_t xy = cand_key_xy(key);   // dropped candidates read 0xFFFFFFFF, outside every box
-                                    const bool hit = (__vminu2(__vmaxu2(xy, lo0), hi0) == xy) | (__vminu2(__vmaxu2(xy, lo1), hi1) == xy) |
-                                                     (__vminu2(__vmaxu2(xy, lo2), hi2) == xy);
+                                    const uint32_t xy = key_xy(key);
+                                    const bool hit = key != kDeadKey && ((__vminu2(__vmaxu2(xy, lo0), hi0) == xy) | (__vminu2(__vmaxu2(xy, lo1), hi1) == xy) |
+                                                                         (__vminu2(__vmaxu2(xy, lo2), hi2) == xy));
                                     if (hit) binned[j] = kDeadKey;
                                     else best = min(best, key);
                                 }
                             } else {
                                 for (uint32_t j = js; j < je; j += 8) {
                                     const uint64_t key = binned[j];
-                                    const uint32_t xy = cand_key_xy(key);
+                                    const uint32_t xy = key_xy(key);
                                     const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                                     if (key != kDeadKey && near_kept(cells, pitch, c, x, y, d)) binned[j] = kDeadKey;   // every kept point, fresh or not
                                     else best = min(best, key);
                                 }
                             }
-    #pragma unroll
+#pragma unroll
                             for (int o = 1; o < 8; o <<= 1) best = min(best, __shfl_xor_sync(group_mask, best, o));
                             if (sub == 0) cmin[c] = best;
                             alive |= best != kDeadKey;
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                         uint64_t key = 0ull;
                         if (live) {
                             key = cur[i];
-                            const uint32_t xy = cand_key_xy(key);
+                            const uint32_t xy = key_xy(key);
                             const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                             const int c = cell_of(xy);
                             if (round == 0) {
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     if (m == 0u) break;
                     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
                         const uint64_t key = nxt[i];
-                        const uint32_t xy = cand_key_xy(key);
+                        const uint32_t xy = key_xy(key);
                         const int c = cell_of(xy);
                         if (uint64_t(cmin[c]) != key) continue;
                         if (key < neighbour_min(cmin, pitch, c)) {
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     float4 *kp_out = p.keypoints + int64_t(frame) * p.kp_capacity;
     for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
         const uint64_t key = kept[i];
-        const uint32_t xy = cand_key_xy(key);
+        const uint32_t xy = key_xy(key);
         kp_out[i] = make_float4(float(xy & 0xFFFFu), float(xy >> 16), cand_key_response(key), 0.0f);  // Vec2(pixel.x(), pixel.y()), :67
     }
     if (threadIdx.x == 0) p.kp_counts[frame] = int32_t(n_out);

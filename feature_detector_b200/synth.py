@@ -56,3 +56,31 @@ def tiled_batch(width: int, height: int, n: int, n_unique: int = 64, start: int 
     for i in range(n):
         out[i] = np.roll(base[i % n_unique], shift=(i // n_unique) * 7, axis=0)
     return out
+
+
+def synth_heatmap(width: int, height: int, idx: int, quantum: float = 0.0, seed: int = SEED) -> np.ndarray:
+    """A keypoint heat map of the kind a SuperPoint / DISK head emits, ``(height, width)`` float32 in [0, 1): a low noise
+    floor plus a few hundred narrow peaks.  ``quantum`` > 0 rounds the values to multiples of it, which produces many
+    exactly equal responses (the tie rule of the reference's multimap walk is part of the parity contract)."""
+    rng = np.random.default_rng([seed, width, height, idx, 77])
+    hm = (rng.random((height, width)) ** 6 * 0.12).astype(np.float32)   # a few per cent of the floor clears the default threshold 0.1
+    n_peaks = max(4, (width * height) // 900)
+    ys, xs = rng.integers(0, height, n_peaks), rng.integers(0, width, n_peaks)
+    amp = rng.random(n_peaks).astype(np.float32)
+    for y, x, a in zip(ys, xs, amp):
+        y0, y1, x0, x1 = max(y - 2, 0), min(y + 3, height), max(x - 2, 0), min(x + 3, width)
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        blob = a * np.exp(-0.5 * ((yy - y) ** 2 + (xx - x) ** 2)).astype(np.float32)
+        hm[y0:y1, x0:x1] = np.maximum(hm[y0:y1, x0:x1], blob)
+    if quantum > 0.0:
+        hm = (np.round(hm / np.float32(quantum)) * np.float32(quantum)).astype(np.float32)
+    return np.minimum(hm, np.float32(0.999)).astype(np.float32)
+
+
+def synth_descriptor_volume(channels: int, map_rows: int, map_cols: int, idx: int, seed: int = SEED) -> np.ndarray:
+    """A dense descriptor volume ``(channels, map_rows, map_cols)`` float32 with unit-norm columns, as the descriptor head
+    of a SuperPoint-style model produces at 1/8 resolution."""
+    rng = np.random.default_rng([seed, channels, map_rows, map_cols, idx, 78])
+    vol = rng.standard_normal((channels, map_rows, map_cols)).astype(np.float32)
+    vol /= np.sqrt((vol.astype(np.float64) ** 2).sum(0, keepdims=True)).astype(np.float32)
+    return vol

@@ -190,6 +190,31 @@ fd_status fd_lsd_device_outputs(fd_context *ctx, const float **dev_norm, const f
 fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *host_angle, int32_t *host_sorted_idx, int64_t sorted_capacity,
                           int32_t *host_n_valid);
 
+/* ---- post-processing of a learned detector's outputs ------------------------------------------------
+ * The part of NNFeaturePointDetector that is not the ONNX session (nn_feature_point_detector.cpp): the model runs wherever
+ * the caller runs it and leaves its outputs in device memory.
+ * fd_nn_select_from_heatmap = CreateMask (:59-72) + SelectKeypointCandidatesFromHeatMap (:128-139) +
+ * SelectGoodFeaturesFromCandidates (:141-155) on n_frames row-major rows x cols float heat maps: pixels with response >
+ * min_response, invalid_boundary pixels inside the map and outside the squares of the pre-existing features
+ * (fd_set_existing_features), are walked by response descending -- equal responses: the later raster position first, as
+ * the reference's multimap does -- and kept at min_feature_distance until max_features (pre-existing ones included) is
+ * reached.  Results: fd_download_keypoints / fd_device_keypoints (new features only).
+ * fd_nn_sample_descriptors = ExtractDescriptorsForSelectedFeatures (:163-193) for the keypoints just selected: dev_maps
+ * holds n_frames x channels planes of map_rows x map_cols floats (the model's 1/8-resolution descriptor volume); the
+ * output is `channels` floats per keypoint slot, in dev_out (n_frames * kp_capacity * channels floats) or, if NULL, in a
+ * context-owned buffer that fd_nn_download_descriptors copies out. */
+typedef struct fd_nn_params {
+    float min_response;           /* Options::kMinResponse, default 0.1f (nn_feature_point_detector.h:28) */
+    int32_t invalid_boundary;     /* kInvalidBoundary, default 3 */
+    int32_t min_feature_distance; /* kMinFeatureDistance, default 15 */
+    uint32_t max_features;        /* kMaxNumberOfDetectedFeatures, default 240 */
+    int32_t reserved;             /* must be 0 */
+} fd_nn_params;
+fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, int rows, int cols, int n_frames, const fd_nn_params *params,
+                                    int cand_capacity);
+fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, float *dev_out);
+fd_status fd_nn_download_descriptors(fd_context *ctx, float *host_desc, int kp_capacity);
+
 /* ---- diagnostics of the host-built tables (no GPU needed; used by the CPU test-suite) ------------- */
 /* Bit patterns of the FAST running offset (fast.cpp:85,93) for masked-in pixel index k = 0..count-1, as
  * evaluated from the piecewise-linear table the kernel uses; *n_segments = pieces in that table. */

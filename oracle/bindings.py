@@ -148,6 +148,36 @@ class _Detectors:
             raise RuntimeError(f"{self.prefix}lsd_map failed ({rc})")
         return {"norm": norm, "angle": angle, "valid": valid, "sorted_rc": sorted_rc[:n.value].copy()}
 
+    def nn_select(self, heatmap, min_response=0.1, invalid_boundary=3, min_distance=15, max_features=240, pre=None):
+        """NN detector post-processing on a heat map: returns dict(features (n,2) f32 incl. the pre-existing ones, n_cand)."""
+        hm = np.ascontiguousarray(heatmap, np.float32)
+        rows, cols = hm.shape
+        pre = np.zeros((0, 2), np.float32) if pre is None else np.ascontiguousarray(pre, np.float32).reshape(-1, 2)
+        max_feats = int(max_features) + len(pre) + 8
+        feats = np.zeros((max_feats, 2), np.float32)
+        feats[:len(pre)] = pre
+        n_out, n_cand = C.c_int(0), C.c_int64(0)
+        fn = getattr(self.lib, self.prefix + "nn_select")
+        fn.restype = C.c_int
+        fn.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        if fn(_p(hm, _f32p), rows, cols, float(min_response), int(invalid_boundary), int(min_distance), int(max_features), _p(feats, _f32p), len(pre),
+              max_feats, C.byref(n_out), C.byref(n_cand)) != 1:
+            raise RuntimeError(self.prefix + "nn_select failed")
+        return {"features": feats[:n_out.value].copy(), "n_cand": n_cand.value}
+
+    def nn_descriptors(self, feats_xy, maps):
+        """maps: (channels, map_rows, map_cols) f32; returns (n, channels) f32."""
+        f = np.ascontiguousarray(feats_xy, np.float32).reshape(-1, 2)
+        m = np.ascontiguousarray(maps, np.float32)
+        ch, mr, mc = m.shape
+        out = np.zeros((len(f), ch), np.float32)
+        fn = getattr(self.lib, self.prefix + "nn_descriptors")
+        fn.restype = C.c_int
+        fn.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p]
+        if fn(_p(f, _f32p), len(f), _p(m, _f32p), ch, mr, mc, _p(out, _f32p)) != 1:
+            raise RuntimeError(self.prefix + "nn_descriptors failed")
+        return out
+
     def sparsify(self, feats_xy, rows, cols, need, after, status, grid_rows=12, grid_cols=12):
         f = np.ascontiguousarray(feats_xy, np.float32).reshape(-1, 2)
         st = np.ascontiguousarray(status, np.uint8).copy()

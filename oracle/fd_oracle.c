@@ -447,6 +447,94 @@ int orc_lsd_map(const uint8_t *img, int rows, int cols, float min_norm, float *n
 /* ------------------------------------------------------------------------------------------------
  * CPU timing of the port (bench.py cpu_baseline kind "port"): one scratch set per thread.
  * ---------------------------------------------------------------------------------------------- */
+/* ---- NN detector post-processing (reference src/nn_feature_point_detector/nn_feature_point_detector.cpp) ------------------
+ * orc_nn_select: CreateMask (:59-72, with UpdateMaskByFeatures :85-91 and DrawRectangleInMask :74-83),
+ * SelectKeypointCandidatesFromHeatMap (:128-139) and SelectGoodFeaturesFromCandidates (:141-155).  The reference keeps
+ * the candidates in a std::multimap<float, Pixel> and walks it backwards: response descending, and among equal responses
+ * the LATER insertion (raster order) first. */
+typedef struct {
+    float response;
+    int32_t index; /* raster index: row * cols + col */
+} nn_cand;
+
+static int nn_cand_before(const void *a, const void *b) {
+    const nn_cand *x = (const nn_cand *)a, *y = (const nn_cand *)b;
+    if (x->response != y->response) return x->response > y->response ? -1 : 1;
+    return x->index > y->index ? -1 : (x->index < y->index ? 1 : 0);
+}
+
+static void nn_clear_square(uint8_t *mask, int rows, int cols, int row, int col, int radius) { /* :74-83 */
+    const int r0 = row - radius > 0 ? row - radius : 0, r1 = row + radius < rows - 1 ? row + radius : rows - 1;
+    const int c0 = col - radius > 0 ? col - radius : 0, c1 = col + radius < cols - 1 ? col + radius : cols - 1;
+    for (int r = r0; r <= r1; ++r)
+        for (int c = c0; c <= c1; ++c) mask[(size_t)r * cols + c] = 0;
+}
+
+int orc_nn_select(const float *heatmap, int rows, int cols, float min_response, int invalid_boundary, int min_distance, int max_features,
+                  float *feats_xy, int n_feats_in, int max_feats, int *n_feats_out, int64_t *n_candidates) {
+    uint8_t *mask = (uint8_t *)malloc((size_t)rows * cols);
+    nn_cand *cand = (nn_cand *)malloc(sizeof(nn_cand) * (size_t)rows * cols);
+    if (!mask || !cand) {
+        free(mask);
+        free(cand);
+        return 0;
+    }
+    memset(mask, 1, (size_t)rows * cols);
+    if (invalid_boundary) { /* :62-67 */
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c)
+                if (r < invalid_boundary || r >= rows - invalid_boundary || c < invalid_boundary || c >= cols - invalid_boundary) mask[(size_t)r * cols + c] = 0;
+    }
+    for (int i = 0; i < n_feats_in; ++i) nn_clear_square(mask, rows, cols, (int32_t)feats_xy[2 * i + 1], (int32_t)feats_xy[2 * i], min_distance); /* :85-91 */
+    int64_t n = 0;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c)
+            if (heatmap[(size_t)r * cols + c] > min_response) { /* :133 */
+                cand[n].response = heatmap[(size_t)r * cols + c];
+                cand[n].index = r * cols + c;
+                ++n;
+            }
+    if (n_candidates) *n_candidates = n;
+    qsort(cand, (size_t)n, sizeof(nn_cand), nn_cand_before);
+    int nf = n_feats_in;
+    for (int64_t i = 0; i < n; ++i) { /* :145-153 */
+        const int row = cand[i].index / cols, col = cand[i].index % cols;
+        if (!mask[(size_t)row * cols + col]) continue;
+        if (nf < max_feats) {
+            feats_xy[2 * nf] = (float)col;
+            feats_xy[2 * nf + 1] = (float)row;
+        }
+        ++nf;
+        if (nf >= max_features) break; /* tested after the push, before the square is cleared */
+        nn_clear_square(mask, rows, cols, row, col, min_distance);
+    }
+    *n_feats_out = nf < max_feats ? nf : max_feats;
+    free(mask);
+    free(cand);
+    return 1;
+}
+
+/* ExtractDescriptorsForSelectedFeatures (:163-193): bilinear taps of every channel plane at (y / 8, x / 8); a keypoint whose
+ * 2x2 neighbourhood leaves the plane gets 0 for that channel.  Products and sums in the reference's order, no contraction. */
+int orc_nn_descriptors(const float *feats_xy, int n_feats, const float *maps, int channels, int map_rows, int map_cols, float *out) {
+    for (int i = 0; i < n_feats; ++i) {
+        const float row = feats_xy[2 * i + 1] / 8.0f, col = feats_xy[2 * i] / 8.0f;
+        const int32_t int_row = (int32_t)row, int_col = (int32_t)col;
+        const float sub_row = row - floorf(row), sub_col = col - floorf(col);
+        const float inv_sub_row = 1.0f - sub_row, inv_sub_col = 1.0f - sub_col;
+        const float w0 = inv_sub_col * inv_sub_row, w1 = sub_col * inv_sub_row, w2 = inv_sub_col * sub_row, w3 = sub_col * sub_row;
+        for (int j = 0; j < channels; ++j) {
+            float v = 0.0f;
+            if (!(int_row < 0 || int_row >= map_rows - 1 || int_col < 0 || int_col >= map_cols - 1)) {
+                const float *p = maps + (size_t)j * map_rows * map_cols + (size_t)int_row * map_cols + int_col;
+                v = w0 * p[0] + w1 * p[1] + w2 * p[map_cols] + w3 * p[map_cols + 1];
+            }
+            out[(size_t)i * channels + j] = v;
+        }
+    }
+    return 1;
+}
+
 typedef struct {
     int kind, n_frames, rows, cols, min_distance, fast_n, brief_length, brief_half;
     uint32_t needed;

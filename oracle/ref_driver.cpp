@@ -36,6 +36,7 @@
 #include "feature_point_fast_detector.h"
 #include "feature_point_harris_detector.h"
 #include "feature_point_shi_tomas_detector.h"
+#include "nn_feature_point_detector.h"
 #undef private
 #undef protected
 
@@ -294,6 +295,56 @@ double ref_bench_lsd(const uint8_t *frames, int n_frames, int rows, int cols, fl
         totals[1] = lines.load();
     }
     return t1 - t0;
+}
+
+// NN post-processing: NNFeaturePointDetector::CreateMask + SelectKeypointCandidatesFromHeatMap + SelectGoodFeaturesFromCandidates
+// (nn_feature_point_detector.cpp:59-72, 128-155) on a heat map, without any model behind it (the ONNX session is a stand-in).
+//  feats_xy  in/out (x, y) float pairs; the first n_feats_in are pre-existing features.  Returns 1, or 0 on failure.
+int ref_nn_select(const float *heatmap, int rows, int cols, float min_response, int invalid_boundary, int min_distance, int max_features,
+                  float *feats_xy, int n_feats_in, int max_feats, int *n_feats_out, int64_t *n_candidates) {
+    NNFeaturePointDetector det;
+    det.options().kMinResponse = min_response;
+    det.options().kInvalidBoundary = invalid_boundary;
+    det.options().kMinFeatureDistance = min_distance;
+    det.options().kMaxNumberOfDetectedFeatures = max_features;
+    std::vector<Vec2> features;
+    for (int i = 0; i < n_feats_in; ++i) features.emplace_back(Vec2(feats_xy[2 * i], feats_xy[2 * i + 1]));
+    const GrayImage shape_only(nullptr, rows, cols, false);   // CreateMask reads rows() and cols() only
+    if (!det.CreateMask(shape_only, features)) return 0;
+    MatImgF map;
+    map.resize(rows, cols);
+    std::memcpy(map.data(), heatmap, sizeof(float) * size_t(rows) * cols);
+    if (!det.SelectKeypointCandidatesFromHeatMap(map)) return 0;
+    if (n_candidates != nullptr) *n_candidates = int64_t(det.candidates_.size());
+    if (!det.SelectGoodFeaturesFromCandidates(features)) return 0;
+    const int n = std::min<int>(int(features.size()), max_feats);
+    for (int i = 0; i < n; ++i) {
+        feats_xy[2 * i] = features[i].x();
+        feats_xy[2 * i + 1] = features[i].y();
+    }
+    *n_feats_out = n;
+    return 1;
+}
+
+// NNFeaturePointDetector::ExtractDescriptorsForSelectedFeatures (nn_feature_point_detector.cpp:163-193): `maps` holds
+// `channels` (256 = SuperPoint, 128 = DISK) row-major map_rows x map_cols planes; out is n_feats x channels.
+int ref_nn_descriptors(const float *feats_xy, int n_feats, const float *maps, int channels, int map_rows, int map_cols, float *out) {
+    NNFeaturePointDetector det;
+    std::vector<Vec2> features;
+    for (int i = 0; i < n_feats; ++i) features.emplace_back(Vec2(feats_xy[2 * i], feats_xy[2 * i + 1]));
+    std::vector<Eigen::Map<const MatImgF>> planes;
+    for (int c = 0; c < channels; ++c) planes.emplace_back(maps + size_t(c) * map_rows * map_cols, map_rows, map_cols);
+    auto run = [&](auto tag) {
+        using D = decltype(tag);
+        std::vector<D> desc;
+        if (!det.ExtractDescriptorsForSelectedFeatures(features, planes, desc)) return 0;
+        for (int i = 0; i < n_feats; ++i)
+            for (int c = 0; c < channels; ++c) out[size_t(i) * channels + c] = desc[i](c);
+        return 1;
+    };
+    if (channels == 256) return run(SuperpointDescriptorType());
+    if (channels == 128) return run(DiskDescriptorType());
+    return 0;
 }
 
 const char *ref_build_info() { return "reference .cpp compiled in place; g++ -std=c++17 -O3 -g -pthread (CMakeLists.txt:6) + -fPIC -shared"; }

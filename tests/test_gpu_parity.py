@@ -567,3 +567,69 @@ def test_host_pipeline_equals_single_call(ctx, torch_cuda):
             assert np.array_equal(cnt, cnt_ref)
             for f in range(21):
                 assert np.array_equal(kp[f, :cnt[f]], kp_ref[f, :cnt[f]]) and np.array_equal(desc[f, :cnt[f]], desc_ref[f, :cnt[f]])
+
+
+# ---- NN detector post-processing (fd_nn.cu) ----------------------------------------------------------------------------------
+def test_nn_postprocessing_vs_checker(ctx, checker, torch_cuda):
+    """Heat map -> candidates -> greedy selection -> descriptor sampling against nn_feature_point_detector.cpp compiled in
+    place: keypoints identical (equal responses included: the later raster position first), descriptors bit-exact."""
+    from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+    torch = torch_cuda
+    rng = np.random.default_rng(21)
+    for trial, (w, h, n_frames) in enumerate([(752, 480, 3), (333, 217, 4), (160, 120, 6), (64, 40, 2)]):
+        for q in (0.0, 1.0 / 32):
+            maps = np.stack([synth_heatmap(w, h, 40 + trial * 10 + f, q) for f in range(n_frames)])
+            d_maps = torch.from_numpy(maps).cuda()
+            pres = [np.stack([rng.integers(0, w, 5 + f), rng.integers(0, h, 5 + f)], 1).astype(np.float32) for f in range(n_frames)]
+            for thr, b, dist, n, with_pre in ((0.1, 3, 15, 240, False), (0.05, 3, 9, 120, True), (0.3, 0, 2, 1000, False), (0.02, 9, 40, 5, True),
+                                              (0.1, 3, 15, 0, False)):
+                ctx.set_existing_features(pres if with_pre else [])
+                ctx.nn_select(d_maps.data_ptr(), h, w, n_frames, fd.NnParams(thr, b, dist, n), 0)
+                kp, cnt = ctx.keypoints(max(n, 1))
+                feats = []
+                for f in range(n_frames):
+                    o = checker.nn_select(maps[f], thr, b, dist, n, pres[f] if with_pre else None)
+                    new = o["features"][len(pres[f]) if with_pre else 0:]
+                    got = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
+                    assert np.array_equal(got, new), (trial, q, thr, f)
+                    assert np.array_equal(kp["response"][f, :cnt[f]], maps[f][got[:, 1].astype(int), got[:, 0].astype(int)])
+                    feats.append(got)
+                for ch in (256, 128):
+                    vol = np.stack([synth_descriptor_volume(ch, h // 8, w // 8, trial + f) for f in range(n_frames)])
+                    d_vol = torch.from_numpy(vol).cuda()
+                    ctx.nn_sample_descriptors(d_vol.data_ptr(), ch, h // 8, w // 8)
+                    desc = ctx.nn_descriptors(max(n, 1))
+                    for f in range(n_frames):
+                        exp = checker.nn_descriptors(feats[f], vol[f])
+                        assert np.array_equal(desc[f, :cnt[f]].view(np.uint32), exp.view(np.uint32)), (trial, q, thr, f, ch)
+    ctx.set_existing_features([])
+
+
+def test_nn_postprocessing_golden(ctx, torch_cuda):
+    import os
+    import importlib.util
+    from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_golden_nn", os.path.join(here, "golden", "make_golden_nn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(here, "golden", "nn_vectors.npz"))
+    torch = torch_cuda
+    for name, w, h, idx, q, thr, b, d, n, n_pre, ch in mod.CASES:
+        hm = synth_heatmap(w, h, idx, q)
+        pre = mod.pre_features(w, h, n_pre, idx) if n_pre else None
+        ctx.set_existing_features([pre] if n_pre else [])
+        d_hm = torch.from_numpy(hm[None]).cuda()
+        ctx.nn_select(d_hm.data_ptr(), h, w, 1, fd.NnParams(thr, b, d, n), 0)
+        kp, cnt = ctx.keypoints(n)
+        got = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32)
+        assert np.array_equal(got, gold[name + ".features"][n_pre:]), name
+        vol = synth_descriptor_volume(ch, h // 8, w // 8, idx)
+        d_vol = torch.from_numpy(vol[None]).cuda()
+        ctx.nn_sample_descriptors(d_vol.data_ptr(), ch, h // 8, w // 8)
+        desc = ctx.nn_descriptors(n)[0, :cnt[0]]
+        # the golden checksum covers the pre-existing features' descriptors too: sample those through the same kernel path
+        if n_pre == 0:
+            assert np.array_equal(desc[:4].view(np.uint32), gold[name + ".desc_first"].view(np.uint32)), name
+            assert np.array_equal(desc.astype(np.float64).sum(0), gold[name + ".desc_sum"]), name
+    ctx.set_existing_features([])

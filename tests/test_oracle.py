@@ -5,6 +5,8 @@
   does not exist;
 * where oracle/_ref is present, port and reference are also compared directly on more frames.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -149,3 +151,44 @@ def test_edge_cases_port(port):
         tiny = np.zeros(shape, np.uint8)
         for kind in (HARRIS, SHI_TOMAS, FAST):
             assert port.detect(kind, tiny, 10, 5, 10)["n_cand"] == 0
+
+
+# ---- NN detector post-processing (nn_feature_point_detector.cpp:59-72, 128-155, 163-193) ----------------------------------
+def _nn_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_nn", os.path.join(os.path.dirname(__file__), "golden", "make_golden_nn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.CASES, mod.pre_features
+
+
+def test_port_reproduces_golden_nn_postprocessing(port):
+    """The committed vectors come from the reference's own nn_feature_point_detector.cpp (tests/golden/make_golden_nn.py)."""
+    from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "nn_vectors.npz"))
+    cases, pre_features = _nn_cases()
+    for name, w, h, idx, q, thr, b, d, n, n_pre, ch in cases:
+        hm = synth_heatmap(w, h, idx, q)
+        pre = pre_features(w, h, n_pre, idx) if n_pre else None
+        sel = port.nn_select(hm, thr, b, d, n, pre)
+        assert sel["n_cand"] == int(gold[name + ".n_cand"]), name
+        assert np.array_equal(sel["features"], gold[name + ".features"]), name
+        desc = port.nn_descriptors(sel["features"], synth_descriptor_volume(ch, h // 8, w // 8, idx))
+        assert np.array_equal(desc[:4].view(np.uint32), gold[name + ".desc_first"].view(np.uint32)), name
+        assert np.array_equal(desc.astype(np.float64).sum(0), gold[name + ".desc_sum"]), name
+
+
+def test_port_equals_reference_nn_postprocessing(port, ref):
+    from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+    rng = np.random.default_rng(3)
+    for trial, (w, h) in enumerate([(160, 120), (97, 61), (240, 136), (64, 64)]):
+        for q in (0.0, 0.125):
+            hm = synth_heatmap(w, h, 10 + trial, q)
+            pre = np.stack([rng.integers(0, w, 6), rng.integers(0, h, 6)], 1).astype(np.float32) if trial % 2 else None
+            for thr, b, d, n in ((0.1, 3, 15, 240), (0.3, 0, 2, 30), (0.02, 9, 40, 5)):
+                a, c = ref.nn_select(hm, thr, b, d, n, pre), port.nn_select(hm, thr, b, d, n, pre)
+                assert a["n_cand"] == c["n_cand"] and np.array_equal(a["features"], c["features"]), (trial, q, thr)
+            for ch in (256, 128):
+                vol = synth_descriptor_volume(ch, h // 8, w // 8, trial)
+                pts = np.concatenate([a["features"], np.array([[0, 0], [w - 1, h - 1], [w - 9, 3], [3.5, 7.25]], np.float32)])
+                assert np.array_equal(ref.nn_descriptors(pts, vol).view(np.uint32), port.nn_descriptors(pts, vol).view(np.uint32))
