@@ -380,6 +380,26 @@ def main():
         keep = named("configs[4] lsd field + seed order, 1920x1080 x 64", 1920, 1080, 64, lambda: ctx.lsd_field(lsd_sorted), 9.2)
         del keep
 
+        # ---- NN detector post-processing: heat maps -> keypoints -> sampled 256-channel descriptors ----
+        from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+        n_nn = min(n, 1024)
+        heat = torch.from_numpy(np.stack([synth_heatmap(W, H, rank * 8 + i) for i in range(8)])).to(dev)
+        heat = heat.repeat((n_nn + 7) // 8, 1, 1)[:n_nn].contiguous()
+        vol = torch.from_numpy(np.stack([synth_descriptor_volume(256, H // 8, W // 8, i) for i in range(2)])).to(dev)
+        vol = vol.repeat((n_nn + 1) // 2, 1, 1, 1)[:n_nn].contiguous()
+        nn_prm = fd.NnParams(0.1, 3, 15, 240)
+
+        def nn_step():
+            ctx.nn_select(heat.data_ptr(), H, W, n_nn, nn_prm, 65536)
+            ctx.nn_sample_descriptors(vol.data_ptr(), 256, H // 8, W // 8)
+        s_nn = timed(nn_step, steps2, 2)
+        ctx.sync()
+        extras["nn post-processing (heat map -> 240 keypoints -> 256-channel descriptors), 752x480 x %d" % n_nn] = {
+            "mpixel_s": round(world * n_nn * px * steps2 / s_nn / 1e6, 1), "frames_s": round(world * n_nn * steps2 / s_nn, 1),
+            "ms_per_step": round(s_nn / steps2 * 1e3, 3), "mean_keypoints": float(ctx.keypoint_counts().mean()),
+            "hbm_frac": round(n_nn * px * 4 * steps2 / s_nn / 1e9 / peak, 4), "bytes_per_px": 4.0}
+        del heat, vol
+
     if rank == 0:
         line = {
             "metric": "Mpixel/s (FAST+NMS+BRIEF, 752x480)", "value": round(value, 2), "unit": "Mpixel/s",

@@ -119,6 +119,8 @@ def load_library():
         "fd_nn_select_from_heatmap": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(NnParams), C.c_int]),
         "fd_nn_sample_descriptors": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
         "fd_nn_download_descriptors": (C.c_int, [vp, vp, C.c_int]),
+        "fd_nn_sample_descriptors_at": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                                  C.POINTER(C.c_float)]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
         "fd_debug_fast_offset_bits": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), i32p]),
@@ -336,6 +338,21 @@ class Context:
         d = np.zeros((self.n_frames, kp_capacity, self._nn_channels), np.float32)
         self._ck(self._lib.fd_nn_download_descriptors(self._h, d.ctypes.data_as(C.c_void_p), kp_capacity))
         return d
+
+    def nn_descriptors_at(self, dev_maps: int, channels: int, map_rows: int, map_cols: int, per_frame_xy):
+        """Descriptors at caller-supplied points: list (one entry per frame) of (k, 2) float arrays -> list of (k, channels) float32."""
+        cap = max(1, max(len(np.asarray(p).reshape(-1, 2)) for p in per_frame_xy))
+        xy = np.zeros((len(per_frame_xy), cap, 2), np.float32)
+        counts = np.zeros(len(per_frame_xy), np.int32)
+        for f, p in enumerate(per_frame_xy):
+            p = np.asarray(p, np.float32).reshape(-1, 2)
+            xy[f, :len(p)] = p
+            counts[f] = len(p)
+        out = np.zeros((len(per_frame_xy), cap, channels), np.float32)
+        self._ck(self._lib.fd_nn_sample_descriptors_at(self._h, C.c_void_p(dev_maps), channels, map_rows, map_cols, xy.ctypes.data_as(C.POINTER(C.c_float)),
+                                                       counts.ctypes.data_as(C.POINTER(C.c_int32)), cap, len(per_frame_xy),
+                                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+        return [out[f, :counts[f]] for f in range(len(per_frame_xy))]
 
     # -- LSD -----------------------------------------------------------------------------------------
     def lsd_field(self, params: LsdParams, dev_norm: int = 0, dev_angle: int = 0, dev_sorted: int = 0, dev_n_valid: int = 0):

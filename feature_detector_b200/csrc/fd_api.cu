@@ -74,7 +74,7 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf nn_desc;
+    DevBuf nn_desc, nn_user_desc;
     int nn_channels = 0;
     bool have_nn_desc = false;
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed, lsd_item_counts, lsd_chunk_sum;
@@ -543,7 +543,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -961,6 +961,43 @@ fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int c
     ++ctx->launches;
     ctx->nn_channels = channels;
     ctx->have_nn_desc = (dev_out == ctx->nn_desc.ptr);
+    return FD_OK;
+}
+
+fd_status fd_nn_sample_descriptors_at(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, const float *host_xy,
+                                      const int32_t *host_counts, int capacity, int n_frames, float *host_out) {
+    if (!ctx || !dev_maps || !host_xy || !host_counts || !host_out || channels <= 0 || map_rows <= 0 || map_cols <= 0 || capacity <= 0 || n_frames <= 0)
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_nn_sample_descriptors_at: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<float4> staged(size_t(n_frames) * capacity, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int f = 0; f < n_frames; ++f) {
+        if (host_counts[f] < 0 || host_counts[f] > capacity) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "point count exceeds capacity");
+        for (int i = 0; i < host_counts[f]; ++i) {
+            const size_t s = size_t(f) * capacity + i;
+            staged[s] = make_float4(host_xy[2 * s], host_xy[2 * s + 1], 0.f, 0.f);
+        }
+    }
+    const size_t out_bytes = size_t(n_frames) * capacity * channels * 4;
+    FD_TRY(reserve(ctx, ctx->user_kp, staged.size() * sizeof(float4)));
+    FD_TRY(reserve(ctx, ctx->user_counts, size_t(n_frames) * 4));
+    FD_TRY(reserve(ctx, ctx->nn_user_desc, out_bytes));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->user_kp.ptr, staged.data(), staged.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->user_counts.ptr, host_counts, size_t(n_frames) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->nn_user_desc.ptr, 0, out_bytes, ctx->stream));   // unused slots read as zeros
+    NnDescriptorArgs a = {};
+    a.maps = dev_maps;
+    a.channels = channels;
+    a.map_rows = map_rows;
+    a.map_cols = map_cols;
+    a.n_frames = n_frames;
+    a.keypoints = static_cast<const float4 *>(ctx->user_kp.ptr);
+    a.kp_counts = static_cast<const int32_t *>(ctx->user_counts.ptr);
+    a.kp_capacity = capacity;
+    a.out = static_cast<float *>(ctx->nn_user_desc.ptr);
+    FD_CUDA(ctx, launch_nn_descriptors(a, ctx->stream));
+    ++ctx->launches;
+    FD_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->nn_user_desc.ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `staged` is pageable host memory going out of scope
     return FD_OK;
 }
 

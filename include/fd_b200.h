@@ -214,6 +214,11 @@ fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, i
                                     int cand_capacity);
 fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, float *dev_out);
 fd_status fd_nn_download_descriptors(fd_context *ctx, float *host_desc, int kp_capacity);
+/* The same sampling at caller-supplied points (the reference describes the pre-existing features too, :166): counts[f]
+ * points for frame f at xy[(f*capacity + i)*2] (host memory); host_out receives n_frames*capacity*channels floats
+ * (unused slots zero).  Synchronises. */
+fd_status fd_nn_sample_descriptors_at(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, const float *host_xy,
+                                      const int32_t *host_counts, int capacity, int n_frames, float *host_out);
 
 /* ---- diagnostics of the host-built tables (no GPU needed; used by the CPU test-suite) ------------- */
 /* Bit patterns of the FAST running offset (fast.cpp:85,93) for masked-in pixel index k = 0..count-1, as

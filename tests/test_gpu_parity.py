@@ -602,6 +602,11 @@ def test_nn_postprocessing_vs_checker(ctx, checker, torch_cuda):
                     for f in range(n_frames):
                         exp = checker.nn_descriptors(feats[f], vol[f])
                         assert np.array_equal(desc[f, :cnt[f]].view(np.uint32), exp.view(np.uint32)), (trial, q, thr, f, ch)
+                    if with_pre:   # the reference describes the pre-existing features too; fractional and border points included
+                        pts = [np.concatenate([pres[f], np.array([[0, 0], [w - 1, h - 1], [3.5, 7.25], [w - 9, 2]], np.float32)]) for f in range(n_frames)]
+                        got = ctx.nn_descriptors_at(d_vol.data_ptr(), ch, h // 8, w // 8, pts)
+                        for f in range(n_frames):
+                            assert np.array_equal(got[f].view(np.uint32), checker.nn_descriptors(pts[f], vol[f]).view(np.uint32)), (trial, f, ch)
     ctx.set_existing_features([])
 
 
