@@ -116,6 +116,8 @@ def load_library():
         "fd_download_descriptors": (C.c_int, [vp, vp, C.c_int]),
         "fd_device_descriptors": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int)]),
         "fd_lsd_field": (C.c_int, [vp, C.POINTER(LsdParams), vp, vp, vp, vp]),
+        "fd_descriptors_as_float": (C.c_int, [vp, vp]),
+        "fd_download_descriptors_float": (C.c_int, [vp, vp, C.c_int]),
         "fd_nn_select_from_heatmap": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(NnParams), C.c_int]),
         "fd_nn_sample_descriptors": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
         "fd_nn_download_descriptors": (C.c_int, [vp, vp, C.c_int]),
@@ -316,6 +318,13 @@ class Context:
         """(n_frames, kp_capacity, 32) uint8; bit i of a descriptor is (byte i//8 >> i%8) & 1."""
         d = np.zeros((self.n_frames, kp_capacity, 32), np.uint8)
         self._ck(self._lib.fd_download_descriptors(self._h, d.ctypes.data_as(C.c_void_p), kp_capacity))
+        return d
+
+    def descriptors_float(self, kp_capacity: int, length: int = 256):
+        """(n_frames, kp_capacity, length) float32 of +1 / -1: the std::vector<Vec> overload of Descriptor::Compute (descriptor.h:43-62)."""
+        self._ck(self._lib.fd_descriptors_as_float(self._h, None))
+        d = np.zeros((self.n_frames, kp_capacity, length), np.float32)
+        self._ck(self._lib.fd_download_descriptors_float(self._h, d.ctypes.data_as(C.c_void_p), kp_capacity))
         return d
 
     def descriptors_into(self, desc: np.ndarray):

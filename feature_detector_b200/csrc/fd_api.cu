@@ -53,6 +53,8 @@ struct fd_context {
 
     DevBuf desc;
     int desc_capacity = 0;     // slots per frame of the described set
+    int desc_length = 0;       // kLength of the last description
+    const int32_t *desc_counts = nullptr;   // device counts of the described set
     bool desc_from_user = false;
     bool have_desc = false;
 
@@ -74,7 +76,8 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf nn_desc, nn_user_desc;
+    DevBuf nn_desc, nn_user_desc, desc_float;
+    bool have_desc_float = false;
     int nn_channels = 0;
     bool have_nn_desc = false;
     DevBuf lsd_norm, lsd_angle, lsd_keys, lsd_counts, lsd_sorted, lsd_hist, lsd_start, lsd_bucketed, lsd_item_counts, lsd_chunk_sum;
@@ -543,7 +546,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -820,7 +823,10 @@ static fd_status run_brief(fd_context *ctx, const fd_brief_params *p, const floa
     FD_CUDA(ctx, launch_brief(a, ctx->stream));
     ++ctx->launches;
     ctx->desc_capacity = capacity;
+    ctx->desc_length = p->length;
+    ctx->desc_counts = counts;
     ctx->have_desc = true;
+    ctx->have_desc_float = false;
     return FD_OK;
 }
 
@@ -864,6 +870,34 @@ fd_status fd_download_descriptors(fd_context *ctx, uint8_t *host_desc, int kp_ca
     const int w = std::min(kp_capacity, ctx->desc_capacity);
     FD_CUDA(ctx, cudaMemcpy2DAsync(host_desc, size_t(kp_capacity) * 32, ctx->desc.ptr, size_t(ctx->desc_capacity) * 32, size_t(w) * 32, size_t(nf),
                                    cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+fd_status fd_descriptors_as_float(fd_context *ctx, float *dev_out) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nf = ctx->fv.n_frames;
+    const bool own = dev_out == nullptr;
+    if (own) {
+        FD_TRY(reserve(ctx, ctx->desc_float, size_t(nf) * ctx->desc_capacity * ctx->desc_length * 4));
+        dev_out = static_cast<float *>(ctx->desc_float.ptr);
+    }
+    FD_CUDA(ctx, launch_brief_to_float(static_cast<const uint8_t *>(ctx->desc.ptr), ctx->desc_counts, ctx->desc_capacity, nf, ctx->desc_length, dev_out,
+                                       ctx->stream));
+    ++ctx->launches;
+    if (own) ctx->have_desc_float = true;
+    return FD_OK;
+}
+
+fd_status fd_download_descriptors_float(fd_context *ctx, float *host_desc, int kp_capacity) {
+    if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_desc_float) return fail(ctx, FD_ERR_NOT_READY, "fd_descriptors_as_float has not written to the context's buffer");
+    const size_t row = size_t(ctx->desc_length) * 4;
+    const int w = std::min(kp_capacity, ctx->desc_capacity);
+    FD_CUDA(ctx, cudaMemcpy2DAsync(host_desc, size_t(kp_capacity) * row, ctx->desc_float.ptr, size_t(ctx->desc_capacity) * row, size_t(w) * row,
+                                   size_t(ctx->fv.n_frames), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FD_OK;
 }

@@ -143,6 +143,8 @@ struct BriefArgs {
     uint8_t *desc;             // 32 bytes per keypoint slot
 };
 cudaError_t launch_brief(const BriefArgs &args, cudaStream_t stream);
+// The std::vector<Vec> overload of Descriptor::Compute (descriptor.h:43-62): packed bits -> +1 / -1 floats, `length` per keypoint slot.
+cudaError_t launch_brief_to_float(const uint8_t *desc, const int32_t *kp_counts, int kp_capacity, int n_frames, int length, float *out, cudaStream_t stream);
 
 // ---- kernel 5: LSD gradient / level-line field --------------------------------------------------
 constexpr int LSD_THREADS = 256;

@@ -174,6 +174,11 @@ fd_status fd_describe_points(fd_context *ctx, const fd_brief_params *params, con
  * Slot layout follows the keypoints that were described. */
 fd_status fd_download_descriptors(fd_context *ctx, uint8_t *host_desc, int kp_capacity);
 fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *kp_capacity);
+/* The std::vector<Vec> overload of Descriptor::Compute (descriptor.h:43-62) for the descriptors just computed: bit set -> +1.0f,
+ * clear -> -1.0f, kLength floats per keypoint slot, into dev_out (n_frames * kp_capacity * kLength floats, device memory) or,
+ * if NULL, into a context-owned buffer that fd_download_descriptors_float copies out (slots past a frame's count: unspecified). */
+fd_status fd_descriptors_as_float(fd_context *ctx, float *dev_out);
+fd_status fd_download_descriptors_float(fd_context *ctx, float *host_desc, int kp_capacity);
 
 /* ---- kernel 5: FeatureLineDetector::ComputeLineLevelAngleMap (feature_line_detector.cpp:56-97) -- */
 /* For every bound frame: gradient norm and level-line angle maps, written as rows x cols floats, row-major

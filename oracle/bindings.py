@@ -130,6 +130,17 @@ class _Detectors:
                                                      half_patch, _p(bits, _u8p))
         return bool(ok), bits
 
+    def brief_vec(self, img, kp_xy, length=256, half_patch=8):
+        """The std::vector<Vec> overload: returns (ok, (n, length) float32 of +1 / -1)."""
+        img = _img(img)
+        kp = np.ascontiguousarray(kp_xy, np.float32).reshape(-1, 2)
+        out = np.zeros((len(kp), length), np.float32)
+        fn = getattr(self.lib, self.prefix + "brief_vec")
+        fn.restype = C.c_int
+        fn.argtypes = [_u8p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p]
+        ok = fn(_p(img, _u8p), img.shape[0], img.shape[1], _p(kp, _f32p), len(kp), length, half_patch, _p(out, _f32p))
+        return bool(ok), out
+
     # -- LSD map --------------------------------------------------------------------------------
     def lsd_map(self, img, min_norm=20.0):
         """Returns dict(norm, angle, valid ((rows-1),(cols-1)), sorted_rc (n,2))."""

@@ -447,6 +447,17 @@ int orc_lsd_map(const uint8_t *img, int rows, int cols, float min_norm, float *n
 /* ------------------------------------------------------------------------------------------------
  * CPU timing of the port (bench.py cpu_baseline kind "port"): one scratch set per thread.
  * ---------------------------------------------------------------------------------------------- */
+/* Descriptor<T>::Compute, std::vector<Vec> overload (reference src/feature_descriptor/descriptor.h:43-62): +1 / -1 per bit. */
+int orc_brief_vec(const uint8_t *img, int rows, int cols, const float *kp_xy, int n, int length, int half_patch, float *out) {
+    uint8_t *bits = (uint8_t *)malloc((size_t)(n > 0 ? n : 1) * length);
+    if (!bits) return 0;
+    const int ok = orc_brief(img, rows, cols, kp_xy, n, length, half_patch, bits);
+    if (ok)
+        for (size_t i = 0; i < (size_t)n * length; ++i) out[i] = bits[i] ? 1.0f : -1.0f;
+    free(bits);
+    return ok;
+}
+
 /* ---- NN detector post-processing (reference src/nn_feature_point_detector/nn_feature_point_detector.cpp) ------------------
  * orc_nn_select: CreateMask (:59-72, with UpdateMaskByFeatures :85-91 and DrawRectangleInMask :74-83),
  * SelectKeypointCandidatesFromHeatMap (:128-139) and SelectGoodFeaturesFromCandidates (:141-155).  The reference keeps

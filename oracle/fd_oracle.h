@@ -16,6 +16,7 @@ int orc_lsd_map(const uint8_t *img, int rows, int cols, float min_norm, float *n
                 int64_t max_sorted, int64_t *n_sorted);
 void orc_sparsify(const float *feats_xy, int n, int rows, int cols, int grid_rows, int grid_cols, uint8_t need, uint8_t after,
                   uint8_t *status, int n_status);
+int orc_brief_vec(const uint8_t *img, int rows, int cols, const float *kp_xy, int n, int length, int half_patch, float *out);
 int orc_nn_select(const float *heatmap, int rows, int cols, float min_response, int invalid_boundary, int min_distance, int max_features,
                   float *feats_xy, int n_feats_in, int max_feats, int *n_feats_out, int64_t *n_candidates);
 int orc_nn_descriptors(const float *feats_xy, int n_feats, const float *maps, int channels, int map_rows, int map_cols, float *out);

@@ -146,6 +146,21 @@ int ref_brief(const uint8_t *img, int rows, int cols, const float *kp_xy, int n,
     return 1;
 }
 
+// Descriptor<BriefType>::Compute, std::vector<Vec> overload (descriptor.h:43-62) -> n * length floats (+1 / -1).
+int ref_brief_vec(const uint8_t *img, int rows, int cols, const float *kp_xy, int n, int length, int half_patch, float *out) {
+    BriefDescriptor desc;
+    desc.options().kLength = length;
+    desc.options().kHalfPatchSize = half_patch;
+    GrayImage image(const_cast<uint8_t *>(img), rows, cols, false);
+    std::vector<Vec2> uv;
+    for (int i = 0; i < n; ++i) uv.emplace_back(Vec2(kp_xy[2 * i], kp_xy[2 * i + 1]));
+    std::vector<Vec> vecs;
+    if (!desc.Compute(image, uv, vecs)) return 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < length; ++j) out[size_t(i) * length + j] = vecs[i](j);
+    return 1;
+}
+
 // The 256x4 pattern table (descriptor_brief.cpp:52-309) as the reference holds it in memory.
 void ref_brief_pattern(int16_t *out_1024) {
     for (int i = 0; i < 1024; ++i) out_1024[i] = BriefDescriptor::pattern_idx_[i];

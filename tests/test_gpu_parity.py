@@ -213,6 +213,20 @@ def test_brief_golden_and_checker(ctx, checker, frames, kat, vectors):
         assert ok and np.array_equal(bits, exp), (length, hp)
 
 
+def test_brief_float_overload(ctx, checker, frames):
+    """The std::vector<Vec> overload of Descriptor::Compute (descriptor.h:43-62) on the device: +1 / -1 per bit."""
+    for name, im in frames.items():
+        for length in (256, 100):
+            ctx.upload(im)
+            ctx.detect(fd.DetectParams(fd.HARRIS, 20.0, 20, 80))
+            ctx.describe_selected(fd.BriefParams(length, 8))
+            kp, cnt = ctx.keypoints(80)
+            got = ctx.descriptors_float(80, length)[0, :cnt[0]]
+            pts = np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32)
+            ok, exp = checker.brief_vec(im, pts, length)
+            assert ok and np.array_equal(got, exp), (name, length)
+
+
 def test_detect_then_describe_stays_on_device(ctx, checker, image_png):
     """FAST -> select -> BRIEF without a host round trip (config 1 pipeline), against the checker run stage by stage."""
     ctx.upload(image_png)

@@ -192,3 +192,13 @@ def test_port_equals_reference_nn_postprocessing(port, ref):
                 vol = synth_descriptor_volume(ch, h // 8, w // 8, trial)
                 pts = np.concatenate([a["features"], np.array([[0, 0], [w - 1, h - 1], [w - 9, 3], [3.5, 7.25]], np.float32)])
                 assert np.array_equal(ref.nn_descriptors(pts, vol).view(np.uint32), port.nn_descriptors(pts, vol).view(np.uint32))
+
+
+def test_brief_vec_overload_port_equals_reference(port, ref, image_png):
+    """descriptor.h:43-62: the float overload maps bits to +1 / -1."""
+    kp = ref.detect(HARRIS, image_png, 20, 20, 60, want_candidates=False)["features"]
+    for length in (256, 100):
+        ok_a, a = ref.brief_vec(image_png, kp, length)
+        ok_b, b = port.brief_vec(image_png, kp, length)
+        assert ok_a and ok_b and np.array_equal(a, b)
+        assert np.array_equal(a > 0, ref.brief(image_png, kp, length)[1].astype(bool)) and set(np.unique(a)) <= {-1.0, 1.0}
