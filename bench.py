@@ -372,9 +372,9 @@ def main():
         keep = named("configs[2] shi_tomas top-1000, 1280x720 x 256", 1280, 720, 256, lambda: ctx.detect(shi, 131072), 1.0)
         extras["configs[2] shi_tomas top-1000, 1280x720 x 256"]["mean_keypoints"] = float(ctx.keypoint_counts().mean())
         har = fd.DetectParams(fd.HARRIS, 30.0, 20, 200)
-        keep = named("configs[3] harris candidates, 3840x2160 x 16 (untiled, one GPU)", 3840, 2160, 16, lambda: ctx.compute_candidates(har, 1 << 20), 1.8)
-        extras["configs[3] harris candidates, 3840x2160 x 16 (untiled, one GPU)"]["mean_candidates"] = float(ctx.candidate_counts().mean())
-        keep = named("configs[3] harris + select, 3840x2160 x 16", 3840, 2160, 16, lambda: ctx.detect(har, 1 << 20), 1.8)
+        keep = named("configs[3] harris candidates, 3840x2160 x 64 (untiled, one GPU)", 3840, 2160, 64, lambda: ctx.compute_candidates(har, 1 << 20), 1.8)
+        extras["configs[3] harris candidates, 3840x2160 x 64 (untiled, one GPU)"]["mean_candidates"] = float(ctx.candidate_counts().mean())
+        keep = named("configs[3] harris + select, 3840x2160 x 64", 3840, 2160, 64, lambda: ctx.detect(har, 1 << 20), 1.8)
         keep = named("configs[4] lsd field, 1920x1080 x 64", 1920, 1080, 64, lsd_step, 9.0)
         lsd_sorted = fd.LsdParams(20.0, 1)
         keep = named("configs[4] lsd field + seed order, 1920x1080 x 64", 1920, 1080, 64, lambda: ctx.lsd_field(lsd_sorted), 9.2)
