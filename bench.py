@@ -345,6 +345,19 @@ def main():
         measure("harris+select (thr 30, d 20, N 200)", fd.DetectParams(fd.HARRIS, 30.0, 20, 200), 65536, False)
         measure("shi_tomas+select (thr 40, d 20, N 200)", fd.DetectParams(fd.SHI_TOMAS, 40.0, 20, 200), 65536, False)
 
+        # ---- dense-map output modes (reported separately; 1 B/px in + the map out) ----
+        resp_map = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+        score_map = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+        for name, prm, resp_ptr, score_ptr, bpp in (("harris candidates + dense response map (5 B/px)", fd.DetectParams(fd.HARRIS, 30.0, 20, 200), resp_map.data_ptr(), 0, 5.0),
+                                                   ("fast candidates + dense score map (2 B/px)", fd.DetectParams(fd.FAST, THR, DIST, NEEDED, fast_n=args.fast_n), 0, score_map.data_ptr(), 2.0)):
+            ctx.set_dense_outputs(resp_ptr, score_ptr)
+            s_d = timed(lambda: ctx.compute_candidates(prm, 65536), steps2, 2)
+            ctx.sync()
+            extras[name] = {"mpixel_s": round(world * n * px * steps2 / s_d / 1e6, 1), "ms_per_step": round(s_d / steps2 * 1e3, 3),
+                            "hbm_frac": round(n * px * bpp * steps2 / s_d / 1e9 / peak, 4), "bytes_per_px": bpp}
+        ctx.set_dense_outputs(0, 0)
+        del resp_map, score_map
+
         def lsd_step():
             ctx.lsd_field(fd.LsdParams(20.0, 0))
         nl = min(n, 256)
