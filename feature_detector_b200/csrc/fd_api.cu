@@ -396,7 +396,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.absdiff_shift = shift;
             a.absdiff_mask = ((0xFFu << shift) & 0xFFu) * 0x01010101u;
             const bool prunable = precheck ? (a.kmin[0] == 0xFFFFFFFFu && shift >= 1) : (a.kmin[3] == 0xFFFFFFFFu);
-            const bool sparse = prunable && proc_rows > 0 && !ctx->force_dense_fast && mask.bits == nullptr && ctx->score_map == nullptr && ensure_frame_map(ctx);
+            const bool sparse = prunable && proc_rows > 0 && !ctx->force_dense_fast && ctx->score_map == nullptr && ensure_frame_map(ctx);
             int grid;
             if (sparse) {
                 plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);

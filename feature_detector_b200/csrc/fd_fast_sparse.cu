@@ -88,7 +88,10 @@ __device__ __forceinline__ void tma_load_rows(void *dst, const CUtensorMap *map,
 
 enum : int { MODE_ANY = 0, MODE_ADJ = 1 };
 
-template <bool PRECHECK>
+// MASKED: pre-existing features (feature_point_detector.cpp:12-16): masked-out pixels are neither scored nor counted by the running
+// offset (fast.cpp:88), so phase B takes the pixel index from the mask's prefix counts; phase A and the score bounds of a band
+// keep using the raster index, which is never smaller (a larger index only admits lower scores: conservative).
+template <bool PRECHECK, bool MASKED>
 __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(const FastArgs p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ OffsetSeg segs[FAST_MAX_SEGS];
@@ -156,9 +159,16 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
             while (s_band > 0 && p.kmin[s_band - 1] <= k_last) --s_band;
         }
         const uint32_t need_add = (s_band > 16) ? 0u : (0x80u - uint32_t(s_band)) * 0x01010101u;
+        const int mwpr = p.mask.words_per_row;
+        const uint32_t *mbits = nullptr, *mprefix = nullptr, *mrow_base = nullptr;
+        if (MASKED) {
+            mbits = p.mask.bits + int64_t(frame) * fv.rows * mwpr;
+            mprefix = p.mask.word_prefix + int64_t(frame) * fv.rows * mwpr;
+            mrow_base = p.mask.row_base + int64_t(frame) * (fv.rows + 1);
+        }
         int seg_band = 0;
         {
-            const uint32_t k_first = uint32_t(row_begin + abs0 - 3) * uint32_t(inner_cols);
+            const uint32_t k_first = MASKED ? __ldg(mrow_base + row_begin) : uint32_t(row_begin + abs0 - 3) * uint32_t(inner_cols);
             while (k_first >= segs[seg_band + 1].k_start) ++seg_band;
         }
 
@@ -201,22 +211,32 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
                 if (c0 + j >= 3 && c0 + j <= fv.cols - 4) ok |= 0xFFu << (8 * j);
             if (!valid) ok = 0u;
             sp &= ok;
-            const uint32_t able = (sp + need_add) & ok & 0x80808080u;  // score >= s_band: may pass somewhere in the band
+            uint32_t able = (sp + need_add) & ok & 0x80808080u;  // score >= s_band: may pass somewhere in the band
+            uint32_t mword = 0u;
+            if (MASKED && able != 0u) {
+                mword = __ldg(mbits + int64_t(row_begin - 3 + lc) * mwpr + (c0 >> 5));
+                const uint32_t nib = (mword >> (c0 & 31)) & 0xFu;                  // mask bits of this lane's 4 pixels
+                able &= ((nib * 0x00204081u) & 0x01010101u) * 0x80u;               // bit j -> bit 7 of byte j
+            }
             if (__any_sync(0xffffffffu, able != 0u)) {
-                const int r = row_begin - 3 + lc + abs0;   // absolute row
-                const uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols);
-                int sg = seg_band;
-                if (able != 0u) {
-                    const uint32_t k_lo = k_row + uint32_t(max(c0 - 3, 0));
-                    while (k_lo >= segs[sg + 1].k_start) ++sg;
+                const int r = row_begin - 3 + lc + abs0;   // absolute row (masks are never combined with row tiles: abs0 = 0)
+                uint32_t k_row = uint32_t(r - 3) * uint32_t(inner_cols), k_lo = k_row + uint32_t(max(c0 - 3, 0));
+                uint32_t m_interior = 0u;
+                if (MASKED && able != 0u) {
+                    k_row = __ldg(mrow_base + r);
+                    k_lo = k_row + __ldg(mprefix + int64_t(r) * mwpr + (c0 >> 5));   // masked-in interior pixels of the row before this mask word
+                    m_interior = fast_interior_bits(c0 >> 5, fv.cols);
                 }
+                int sg = seg_band;
+                if (able != 0u)
+                    while (k_lo >= segs[sg + 1].k_start) ++sg;
                 uint32_t mine = 0u;
                 float resp[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     resp[j] = 0.0f;
                     if ((able >> (8 * j + 7)) & 1u) {
-                        const uint32_t k = k_row + uint32_t(c0 + j - 3);
+                        const uint32_t k = MASKED ? k_lo + __popc(mword & m_interior & ((1u << ((c0 & 31) + j)) - 1u)) : k_row + uint32_t(c0 + j - 3);
                         int sj = sg;
                         while (k >= segs[sj + 1].k_start) ++sj;
                         const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
@@ -330,21 +350,23 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
 
 size_t fast_sparse_smem_bytes() { return size_t(SP_WARPS) * sizeof(WarpSmem) + 128; }
 
+namespace {
+template <bool PRECHECK, bool MASKED>
+cudaError_t launch_sparse_t(const FastArgs &args, const CUtensorMap &map, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(fast_sparse_kernel<PRECHECK, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    fast_sparse_kernel<PRECHECK, MASKED><<<grid, FAST_SPARSE_THREADS, smem, stream>>>(args, map);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_fast_sparse(const FastArgs &args, const void *tensor_map, bool precheck, int grid, cudaStream_t stream) {
     const size_t smem = fast_sparse_smem_bytes();
     CUtensorMap map;
     memcpy(&map, tensor_map, sizeof(map));
-    cudaError_t e;
-    if (precheck) {
-        e = cudaFuncSetAttribute(fast_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        fast_sparse_kernel<true><<<grid, FAST_SPARSE_THREADS, smem, stream>>>(args, map);
-    } else {
-        e = cudaFuncSetAttribute(fast_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        fast_sparse_kernel<false><<<grid, FAST_SPARSE_THREADS, smem, stream>>>(args, map);
-    }
-    return cudaGetLastError();
+    const bool masked = args.mask.bits != nullptr;
+    if (precheck) return masked ? launch_sparse_t<true, true>(args, map, grid, smem, stream) : launch_sparse_t<true, false>(args, map, grid, smem, stream);
+    return masked ? launch_sparse_t<false, true>(args, map, grid, smem, stream) : launch_sparse_t<false, false>(args, map, grid, smem, stream);
 }
 
 }  // namespace fdb

@@ -501,6 +501,25 @@ def test_fast_sparse_equals_dense_other_diffs_and_batches(ctx, dense_ctx, fast_n
             kp_a, cnt_a = ctx.keypoints(50)
             kp_b, cnt_b = dense_ctx.keypoints(50)
             assert np.array_equal(cnt_a, cnt_b) and np.array_equal(kp_a, kp_b)
+        # with pre-existing features the sparse form takes the pixel index from the mask's prefix counts
+        h, w = frames.shape[1:]
+        existing = [np.stack([rng.integers(0, w, 12 + f), rng.integers(0, h, 12 + f)], 1).astype(np.float32) for f in range(len(frames))]
+        ctx.set_existing_features(existing)
+        dense_ctx.set_existing_features(existing)
+        for diff, thr, d in ((15, 10.0, 20), (15, 8.5, 5), (40, 6.0, 31)):
+            prm = fd.DetectParams(fd.FAST, thr, d, 60, fast_n=fast_n, fast_min_pixel_diff=diff)
+            ctx.detect(prm)
+            dense_ctx.detect(prm)
+            assert np.array_equal(ctx.candidate_counts(), dense_ctx.candidate_counts()), (diff, thr, d)
+            for f in range(len(frames)):
+                assert np.array_equal(_cand_table(ctx, f), _cand_table(dense_ctx, f)), (diff, thr, d, f)
+            kp_a, cnt_a = ctx.keypoints(60)
+            kp_b, cnt_b = dense_ctx.keypoints(60)
+            assert np.array_equal(cnt_a, cnt_b)
+            for f in range(len(frames)):
+                assert np.array_equal(kp_a[f, :cnt_a[f]], kp_b[f, :cnt_b[f]]), (diff, thr, d, f)
+        ctx.set_existing_features([])
+        dense_ctx.set_existing_features([])
 
 
 # ---- the two forms of the selection rounds (fd_select.cu): per live candidate and per cell -------------------------------
