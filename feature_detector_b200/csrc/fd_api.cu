@@ -438,7 +438,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.cand_lo = std::max(a.resp_lo, tile.own_lo);
             a.cand_hi = std::max(a.cand_lo, std::min(a.resp_hi + 1, tile.own_hi));
             int grid;
-            if (mask.bits == nullptr && !ctx->force_stream_corner && a.cand_hi > a.cand_lo && ensure_frame_map(ctx, true)) {
+            if (!ctx->force_stream_corner && a.cand_hi > a.cand_lo && ensure_frame_map(ctx, true)) {
                 plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_TMA_THREADS / 32, 1, 42, 1, a.band_rows, a.n_bands, a.n_items, grid);
                 FD_CUDA(ctx, launch_corner_tma(a, &ctx->corner_map, grid, ctx->stream));
             } else {

@@ -14,7 +14,7 @@
 //     conversion is left before the response;
 //   * the row loop is unrolled over one TMA group (12 rows = 4 turns of the 3-slot register pipeline), so every shared-
 //     memory address is a group base plus a compile-time offset.
-// Used when the frames can be described by a tensor map and no pre-existing-feature mask is set.
+// Used when the frames can be described by a tensor map (with or without a pre-existing-feature mask).
 #include <cuda.h>
 
 #include "fd_corner_common.cuh"
@@ -105,7 +105,7 @@ __device__ __forceinline__ void product_row(SumRow &h, const MagicRow &up, const
     }
 }
 
-template <int KIND>
+template <int KIND, bool MASKED>
 __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const CornerArgs p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ uint8_t smem_raw[];
     const int lane = lane_id();
@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
             n_staged = 0u;
         };
         float *resp_map = p.response_map ? p.response_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
+        // pre-existing features: the response is only evaluated where the mask is set (harris.cpp:94), 0 elsewhere
+        const uint32_t *mbits = MASKED ? p.mask.bits + int64_t(frame) * fv.rows * p.mask.words_per_row + (c0 >> 5) : nullptr;
 
         int s_cur = 0;   // ring slot of the group being processed
         for (int g = 0; g < n_groups; ++g) {
@@ -218,13 +220,20 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                     const int q = n - 2;
                     const bool q_valid = (q >= p.resp_lo && q <= p.resp_hi);
                     float rq[4];
+                    uint32_t mnib = 0xFu;  // mask bits of columns c0 .. c0+3 of row q
+                    if (MASKED) {
+                        if (q_valid && c0 < fv.cols) {
+                            const uint32_t *mp = mbits + int64_t(q) * p.mask.words_per_row;
+                            mnib = __funnelshift_r(__ldg(mp), __ldg(mp + 1), c0 & 31) & 0xFu;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float sxx = __fadd_rn(__fadd_rn(hs[cur].xx[j], hs[p2].xx[j]), hs[p1].xx[j]);  // harris.cpp:81-88,108-116
                         const float syy = __fadd_rn(__fadd_rn(hs[cur].yy[j], hs[p2].yy[j]), hs[p1].yy[j]);
                         const float sxy = __fadd_rn(__fadd_rn(hs[cur].xy[j], hs[p2].xy[j]), hs[p1].xy[j]);
                         const float r = response_of<KIND>(sxx, syy, sxy, p);
-                        rq[j] = (q_valid && col_valid[j]) ? r : 0.0f;
+                        rq[j] = (q_valid && col_valid[j] && ((mnib >> j) & 1u)) ? r : 0.0f;
                     }
                     if (resp_map != nullptr && q >= rb && q < re) {
 #pragma unroll
@@ -280,21 +289,23 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
 
 size_t corner_tma_smem_bytes() { return size_t(CT_WARPS) * sizeof(WarpSmem) + 128; }
 
+namespace {
+template <int KIND, bool MASKED>
+cudaError_t launch_corner_tma_t(const CornerArgs &args, const CUtensorMap &map, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(corner_tma_kernel<KIND, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    corner_tma_kernel<KIND, MASKED><<<grid, CORNER_TMA_THREADS, smem, stream>>>(args, map);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, int grid, cudaStream_t stream) {
     const size_t smem = corner_tma_smem_bytes();
     CUtensorMap map;
     memcpy(&map, tensor_map, sizeof(map));
-    cudaError_t e;
-    if (args.kind == 0) {
-        e = cudaFuncSetAttribute(corner_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        corner_tma_kernel<0><<<grid, CORNER_TMA_THREADS, smem, stream>>>(args, map);
-    } else {
-        e = cudaFuncSetAttribute(corner_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        corner_tma_kernel<1><<<grid, CORNER_TMA_THREADS, smem, stream>>>(args, map);
-    }
-    return cudaGetLastError();
+    const bool masked = args.mask.bits != nullptr;
+    if (args.kind == 0) return masked ? launch_corner_tma_t<0, true>(args, map, grid, smem, stream) : launch_corner_tma_t<0, false>(args, map, grid, smem, stream);
+    return masked ? launch_corner_tma_t<1, true>(args, map, grid, smem, stream) : launch_corner_tma_t<1, false>(args, map, grid, smem, stream);
 }
 
 }  // namespace fdb

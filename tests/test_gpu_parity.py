@@ -522,6 +522,41 @@ def test_fast_sparse_equals_dense_other_diffs_and_batches(ctx, dense_ctx, fast_n
         dense_ctx.set_existing_features([])
 
 
+# ---- the two corner kernels (fd_corner_tma.cu: TMA row ring; fd_corner.cu: register streaming) --------------------------------
+def test_corner_kernels_agree_with_and_without_masks(ctx):
+    """The TMA form is the default; the streaming form serves frames a tensor map cannot describe.  Same candidates and
+    keypoints from both, with and without pre-existing features (the response is 0 where the mask is clear, harris.cpp:94)."""
+    import os
+    from feature_detector_b200.synth import synth
+    os.environ["FD_B200_CORNER_STREAM"] = "1"
+    try:
+        stream_ctx = fd.Context(0)
+    finally:
+        del os.environ["FD_B200_CORNER_STREAM"]
+    try:
+        rng = np.random.default_rng(17)
+        for frames in (np.stack([synth(320, 200, 30 + i) for i in range(5)]), np.stack([synth(752, 480, 90 + i) for i in range(2)]),
+                       rng.integers(0, 256, (3, 67, 131), dtype=np.uint8)):
+            h, w = frames.shape[1:]
+            existing = [np.stack([rng.integers(0, w, 10 + f), rng.integers(0, h, 10 + f)], 1).astype(np.float32) for f in range(len(frames))]
+            for with_existing in (False, True):
+                for kind, thr, d in ((fd.HARRIS, 30.0, 20), (fd.SHI_TOMAS, 40.0, 9), (fd.HARRIS, 0.1, 15)):
+                    tables, kps = [], []
+                    for c in (ctx, stream_ctx):
+                        c.upload(frames)
+                        c.set_existing_features(existing if with_existing else [])
+                        c.detect(fd.DetectParams(kind, thr, d, 150), 0)
+                        tables.append([_cand_table(c, f) for f in range(len(frames))])
+                        kps.append(c.keypoints(150))
+                    for f in range(len(frames)):
+                        assert np.array_equal(tables[0][f], tables[1][f]), (kind, thr, with_existing, f)
+                        n = kps[0][1][f]
+                        assert n == kps[1][1][f] and np.array_equal(kps[0][0][f, :n], kps[1][0][f, :n]), (kind, thr, with_existing, f)
+        ctx.set_existing_features([])
+    finally:
+        stream_ctx.close()
+
+
 # ---- the two forms of the selection rounds (fd_select.cu): per live candidate and per cell -------------------------------
 def _ctx_with_select_threshold(value):
     import os
