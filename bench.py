@@ -368,6 +368,23 @@ def main():
         measure("harris+select (thr 30, d 20, N 200)", fd.DetectParams(fd.HARRIS, 30.0, 20, 200), 65536, False)
         measure("shi_tomas+select (thr 40, d 20, N 200)", fd.DetectParams(fd.SHI_TOMAS, 40.0, 20, 200), 65536, False)
 
+        # ---- one frame at a time, host to host: what a caller of the drop-in classes sees per DetectGoodFeatures + Compute ----
+        one = frames[0]
+        lat = []
+        for i in range(220):
+            t0 = time.perf_counter()
+            ctx.upload(one)
+            ctx.detect(det, CAND_CAPACITY)
+            ctx.describe_selected(brief)
+            ctx.keypoints(NEEDED)
+            ctx.descriptors(NEEDED)
+            if i >= 20:
+                lat.append(time.perf_counter() - t0)
+        extras["single frame, host to host (upload, FAST, selection, BRIEF, download; pageable buffers)"] = {
+            "latency_us_median": round(float(np.median(lat)) * 1e6, 1), "latency_us_p90": round(float(np.percentile(lat, 90)) * 1e6, 1),
+            "mpixel_s": round(px / float(np.median(lat)) / 1e6, 1)}
+        ctx.bind_device(d_frames.data_ptr(), H, W, n)
+
         # ---- dense-map output modes (reported separately; 1 B/px in + the map out) ----
         resp_map = torch.empty((n, H, W), dtype=torch.float32, device=dev)
         score_map = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
