@@ -216,11 +216,21 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
             __syncthreads();
             // neighbouring candidates mostly share a bin (FAST at a low threshold: 3 x 10^5 keys in a dozen bins), so each warp
             // first groups its lanes by bin and the group leader adds the group's size
-            const uint32_t n_warp_rounded = (n + 31u) & ~31u;
-            for (uint32_t i = threadIdx.x; i < n_warp_rounded; i += blockDim.x) {
-                const uint32_t bin = (i < n) ? uint32_t(__ldg(keys + i) >> (64 - SELECT_HIST_BITS)) : 0xFFFFFFFFu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-                if (bin != 0xFFFFFFFFu && lane_id() == __ffs(peers) - 1) atomicAdd(hist + bin, uint32_t(__popc(peers)));
+            // (four keys per thread per trip: the loads of a trip are in flight together -- this pass is pure streaming)
+            for (uint32_t i0 = 0; i0 < n; i0 += 4u * blockDim.x) {
+                uint64_t k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+                    k4[u] = (i < n) ? __ldg(keys + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+                    const uint32_t bin = (i < n) ? uint32_t(k4[u] >> (64 - SELECT_HIST_BITS)) : 0xFFFFFFFFu;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    if (bin != 0xFFFFFFFFu && lane_id() == __ffs(peers) - 1) atomicAdd(hist + bin, uint32_t(__popc(peers)));
+                }
             }
             __syncthreads();
         }
@@ -270,13 +280,18 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                 if (everything) {
                     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(cstart + cell_of(key_xy(__ldg(keys + i))), 1u);
                 } else {
-                    const uint32_t rounded = (n + 31u) & ~31u;   // whole warps enter list_push together
-                    for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
-                        bool live = i < n;
-                        uint64_t key = 0ull;
-                        if (live) {
-                            key = __ldg(keys + i);
-                            live = key >= lower && key < limit;
+                    // four keys per thread per trip (loads in flight together); whole warps enter list_push together
+                    for (uint32_t i0 = 0; i0 < n; i0 += 4u * blockDim.x) {
+                        uint64_t k4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+                            k4[u] = (i < n) ? __ldg(keys + i) : kDeadKey;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint64_t key = k4[u];
+                            bool live = key >= lower && key < limit;   // (the padding key is never below a limit)
                             if (live) {
                                 const uint32_t xy = key_xy(key);
                                 const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
@@ -287,8 +302,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                                 if (live && batch > 0) live = !near_kept(cells, pitch, c, x, y, d);
                                 if (live) atomicAdd(cstart + c, 1u);
                             }
+                            list_push(live, key, admitted_keys, &s_count);
                         }
-                        list_push(live, key, admitted_keys, &s_count);
                     }
                 }
                 __syncthreads();
@@ -377,13 +392,18 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             const uint32_t js = cstart[c - 1] + sub, je = cstart[c];
                             uint64_t best = kDeadKey;
                             if (n_fresh <= 3) {
-                                for (uint32_t j = js; j < je; j += 8) {
-                                    const uint64_t key = binned[j];
-                                    const uint32_t xy = key_xy(key);
-                                    const bool hit = key != kDeadKey && ((__vminu2(__vmaxu2(xy, lo0), hi0) == xy) | (__vminu2(__vmaxu2(xy, lo1), hi1) == xy) |
-                                                                         (__vminu2(__vmaxu2(xy, lo2), hi2) == xy));
-                                    if (hit) binned[j] = kDeadKey;
-                                    else best = min(best, key);
+                                for (uint32_t j = js; j < je; j += 32) {   // four candidates per lane per trip: their loads are in flight together
+                                    uint64_t key[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) key[u] = (j + 8 * u < je) ? binned[j + 8 * u] : kDeadKey;
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const uint32_t xy = key_xy(key[u]);
+                                        const bool hit = key[u] != kDeadKey && ((__vminu2(__vmaxu2(xy, lo0), hi0) == xy) | (__vminu2(__vmaxu2(xy, lo1), hi1) == xy) |
+                                                                                (__vminu2(__vmaxu2(xy, lo2), hi2) == xy));
+                                        if (hit) binned[j + 8 * u] = kDeadKey;
+                                        else best = min(best, key[u]);
+                                    }
                                 }
                             } else {
                                 for (uint32_t j = js; j < je; j += 8) {
