@@ -405,6 +405,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
                     a.n_bands = (proc_rows + a.band_rows - 1) / a.band_rows;
                     a.n_items = int64_t(fv.n_frames) * a.n_strips * a.n_bands;
                 }
+                a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 1;   // flags[1]: zeroed with the overflow flag at the top of this call
                 FD_CUDA(ctx, launch_fast_sparse(a, &ctx->frame_map, precheck, grid, ctx->stream));
             } else {
                 plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);

@@ -109,14 +109,18 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
     __syncthreads();
 
     const FrameView &fv = p.fv;
-    const int64_t total_warps = int64_t(gridDim.x) * SP_WARPS;
-    const int64_t gwarp = int64_t(blockIdx.x) * SP_WARPS + warp;
     const __half2 diff2 = __float2half2_rn(float(p.diff));
     const int inner_cols = fv.cols - 6;
     const uint32_t hm = p.absdiff_mask;   // per byte: bits at or above the largest power of two <= diff + 1
     uint32_t slot_parity = 0u;            // bit s: parity of the phase ring slot s completes next
 
-    for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
+    // Work items are handed out by a global counter (zeroed by the host before the launch), not by a fixed stride: an item's cost
+    // follows its survivor count, and with ~14 items per warp a fixed assignment leaves a visible tail.
+    for (;;) {
+        uint32_t next = 0u;
+        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
+        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (item >= p.n_items) break;
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);

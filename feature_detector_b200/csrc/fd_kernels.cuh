@@ -57,6 +57,7 @@ struct FastArgs {
     MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
     TileView tile;            // row tile of a larger frame (untiled: {0, 0, rows, rows})
     int proc_lo, proc_hi;     // local rows that get scored: [max(3, own_lo), min(rows - 3, own_hi, full_rows - 3 - row_offset))
+    uint32_t *work_counter;   // sparse kernel: next work item to hand out, zero on entry
     uint32_t absdiff_mask;    // sparse kernel: per byte, the bits at or above 2^absdiff_shift
     int absdiff_shift;        // 2^absdiff_shift = largest power of two <= diff + 1
 };
