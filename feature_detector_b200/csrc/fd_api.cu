@@ -76,7 +76,7 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf nn_desc, nn_user_desc, desc_float;
+    DevBuf nn_desc, nn_user_desc, desc_float, lsd_work;
     bool have_desc_float = false;
     int nn_channels = 0;
     bool have_nn_desc = false;
@@ -441,6 +441,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             int grid;
             if (!ctx->force_stream_corner && a.cand_hi > a.cand_lo && ensure_frame_map(ctx, true)) {
                 plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_TMA_THREADS / 32, 1, 42, 1, a.band_rows, a.n_bands, a.n_items, grid);
+                a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 2;   // flags[2]: zeroed at the top of this call
                 FD_CUDA(ctx, launch_corner_tma(a, &ctx->corner_map, grid, ctx->stream));
             } else {
                 plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);
@@ -547,7 +548,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1097,6 +1098,9 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
         a.seed_hist = static_cast<uint32_t *>(ctx->lsd_hist.ptr);
         a.item_counts = static_cast<uint32_t *>(ctx->lsd_item_counts.ptr);
     }
+    FD_TRY(reserve(ctx, ctx->lsd_work, 16));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->lsd_work.ptr, 0, 16, ctx->stream));
+    a.work_counter = static_cast<uint32_t *>(ctx->lsd_work.ptr);
     FD_CUDA(ctx, launch_lsd(a, grid, ctx->stream));
     ++ctx->launches;
     if (params->want_sorted) {

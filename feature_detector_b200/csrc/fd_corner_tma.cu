@@ -121,12 +121,15 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
     __syncthreads();
 
     const FrameView &fv = p.fv;
-    const int64_t total_warps = int64_t(gridDim.x) * CT_WARPS;
-    const int64_t gwarp = int64_t(blockIdx.x) * CT_WARPS + warp;
     const int col_lo = 2, col_hi = fv.cols - 3;
     uint32_t slot_parity = 0u;   // bit s: parity of the phase ring slot s completes next
 
-    for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
+    // work items come from a global counter (zeroed by the host before the launch) rather than a fixed stride: no tail
+    for (;;) {
+        uint32_t next = 0u;
+        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
+        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (item >= p.n_items) break;
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);

@@ -88,6 +88,7 @@ struct CornerArgs {
     int64_t n_items;
     MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
     TileView tile;            // row tile of a larger frame (untiled: {0, 0, rows, rows})
+    uint32_t *work_counter;   // next work item to hand out, zero on entry (TMA form)
     int resp_lo, resp_hi;     // local rows with a defined response, inclusive (harris.cpp:90-92 on the FULL frame)
     int cand_lo, cand_hi;     // local rows that may emit candidates: [cand_lo, cand_hi)
 };
@@ -162,6 +163,7 @@ struct LsdArgs {
     uint32_t *seed_hist;       // with seed_keys: n_frames * LSD_BINS counters, zero on entry (the scatter returns them to zero)
     int n_bands, band_rows;
     int64_t n_items;
+    uint32_t *work_counter;    // next work item to hand out, zero on entry
 };
 cudaError_t launch_lsd(const LsdArgs &args, int grid, cudaStream_t stream);
 // Seed order by exact magnitude binning: scan of the histogram, scatter into buckets, order inside buckets; writes the
