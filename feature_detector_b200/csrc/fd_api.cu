@@ -73,6 +73,7 @@ struct fd_context {
     CUtensorMap frame_map, corner_map;   // [0] box 160 x FAST_SPARSE_GROUP_ROWS (sparse FAST), [1] box 160 x CORNER_TMA_GROUP_ROWS
     bool frame_map_valid = false, frame_map_failed = false, corner_map_valid = false, corner_map_failed = false;
     bool force_stream_corner = false;  // FD_B200_CORNER_STREAM=1: testing knob, always take the register-streaming corner kernel
+    int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
@@ -283,7 +284,7 @@ void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_fr
     grid = ctx->sm_count * ctas_per_sm;
     const int64_t total_warps = int64_t(grid) * warps_per_cta;
     const int64_t base_items = int64_t(n_frames) * n_strips;
-    int64_t want_bands = (8 * total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
+    int64_t want_bands = (ctx->items_per_warp * total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
     want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, std::max(1, interior_rows / min_band)));
     band_rows = int((interior_rows + want_bands - 1) / want_bands);
     band_rows = std::max(band_rows, 1);
@@ -535,6 +536,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     ctx->stream = ctx->own_stream;
     if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
+    if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
