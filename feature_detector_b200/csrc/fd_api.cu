@@ -399,6 +399,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             const bool prunable = precheck ? (a.kmin[0] == 0xFFFFFFFFu && shift >= 1) : (a.kmin[3] == 0xFFFFFFFFu);
             const bool sparse = prunable && proc_rows > 0 && !ctx->force_dense_fast && ctx->score_map == nullptr && ensure_frame_map(ctx);
             int grid;
+            a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 1;   // flags[1]: zeroed with the overflow flag at the top of this call
             if (sparse) {
                 plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_SPARSE_THREADS / 32, 1, 58, 1, a.band_rows, a.n_bands, a.n_items, grid);
                 if (a.band_rows > 2032) {  // the kernel's queue entries keep the band-local row in 11 bits
@@ -406,7 +407,6 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
                     a.n_bands = (proc_rows + a.band_rows - 1) / a.band_rows;
                     a.n_items = int64_t(fv.n_frames) * a.n_strips * a.n_bands;
                 }
-                a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 1;   // flags[1]: zeroed with the overflow flag at the top of this call
                 FD_CUDA(ctx, launch_fast_sparse(a, &ctx->frame_map, precheck, grid, ctx->stream));
             } else {
                 plan_bands(ctx, proc_rows, a.n_strips, fv.n_frames, FAST_THREADS / 32, FAST_CTAS_PER_SM, 14, 1, a.band_rows, a.n_bands, a.n_items, grid);
@@ -440,9 +440,9 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.cand_lo = std::max(a.resp_lo, tile.own_lo);
             a.cand_hi = std::max(a.cand_lo, std::min(a.resp_hi + 1, tile.own_hi));
             int grid;
+            a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 2;   // flags[2]: zeroed at the top of this call
             if (!ctx->force_stream_corner && a.cand_hi > a.cand_lo && ensure_frame_map(ctx, true)) {
                 plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_TMA_THREADS / 32, 1, 42, 1, a.band_rows, a.n_bands, a.n_items, grid);
-                a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 2;   // flags[2]: zeroed at the top of this call
                 FD_CUDA(ctx, launch_corner_tma(a, &ctx->corner_map, grid, ctx->stream));
             } else {
                 plan_bands(ctx, a.cand_hi - a.cand_lo, a.n_strips, fv.n_frames, CORNER_THREADS / 32, 2, 16, 1, a.band_rows, a.n_bands, a.n_items, grid);

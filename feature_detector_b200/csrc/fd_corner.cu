@@ -79,13 +79,15 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
     uint2 *stage2 = reinterpret_cast<uint2 *>(stage);   // little endian: .x = low word of the key, .y = high word
     const FrameView &fv = p.fv;
     const int lane = lane_id();
-    const int warps_per_block = blockDim.x >> 5;
-    const int64_t total_warps = int64_t(gridDim.x) * warps_per_block;
-    const int64_t gwarp = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
     const int row_lo = p.resp_lo, row_hi = p.resp_hi;  // rows with a defined response (bound = 2, harris.cpp:90-92)
     const int col_lo = 2, col_hi = fv.cols - 3;
 
-    for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
+    // work items come from a global counter (zeroed by the host before the launch) rather than a fixed stride: no tail
+    for (;;) {
+        uint32_t next = 0u;
+        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
+        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (item >= p.n_items) break;
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;
         const int band = int(t % p.n_bands);

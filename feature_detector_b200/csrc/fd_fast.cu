@@ -45,14 +45,16 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
 
     const FrameView &fv = p.fv;
     const int lane = lane_id();
-    const int warps_per_block = blockDim.x >> 5;
-    const int64_t total_warps = int64_t(gridDim.x) * warps_per_block;
-    const int64_t gwarp = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
     const __half2 diff2 = __float2half2_rn(float(p.diff));
     const int inner_cols = fv.cols - 6;
     const int last_row = fv.rows - 1;
 
-    for (int64_t item = gwarp; item < p.n_items; item += total_warps) {
+    // work items come from a global counter (zeroed by the host before the launch) rather than a fixed stride: no tail
+    for (;;) {
+        uint32_t next = 0u;
+        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
+        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (item >= p.n_items) break;
         // item -> (frame, band, strip); strips fastest so neighbouring warps share L1 lines
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;

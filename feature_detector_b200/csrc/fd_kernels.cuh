@@ -57,7 +57,7 @@ struct FastArgs {
     MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
     TileView tile;            // row tile of a larger frame (untiled: {0, 0, rows, rows})
     int proc_lo, proc_hi;     // local rows that get scored: [max(3, own_lo), min(rows - 3, own_hi, full_rows - 3 - row_offset))
-    uint32_t *work_counter;   // sparse kernel: next work item to hand out, zero on entry
+    uint32_t *work_counter;   // next work item to hand out, zero on entry
     uint32_t absdiff_mask;    // sparse kernel: per byte, the bits at or above 2^absdiff_shift
     int absdiff_shift;        // 2^absdiff_shift = largest power of two <= diff + 1
 };
@@ -88,7 +88,7 @@ struct CornerArgs {
     int64_t n_items;
     MaskView mask;            // pre-existing features (bits == nullptr: every pixel masked in)
     TileView tile;            // row tile of a larger frame (untiled: {0, 0, rows, rows})
-    uint32_t *work_counter;   // next work item to hand out, zero on entry (TMA form)
+    uint32_t *work_counter;   // next work item to hand out, zero on entry
     int resp_lo, resp_hi;     // local rows with a defined response, inclusive (harris.cpp:90-92 on the FULL frame)
     int cand_lo, cand_hi;     // local rows that may emit candidates: [cand_lo, cand_hi)
 };
