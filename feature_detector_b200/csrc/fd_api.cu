@@ -823,6 +823,7 @@ static fd_status run_brief(fd_context *ctx, const fd_brief_params *p, const floa
     a.length = p->length;
     a.half_patch = p->half_patch_size;
     a.sampling = p->sampling;
+    a.integral_keypoints = ctx->desc_from_user ? 0 : 1;   // selected keypoints are pixel positions; caller-supplied ones may be fractional
     a.desc = static_cast<uint8_t *>(ctx->desc.ptr);
     FD_CUDA(ctx, launch_brief(a, ctx->stream));
     ++ctx->launches;

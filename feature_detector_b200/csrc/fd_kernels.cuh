@@ -142,6 +142,7 @@ struct BriefArgs {
     const int32_t *kp_counts;
     int kp_capacity;
     int length, half_patch, sampling;
+    int integral_keypoints;    // 1: the keypoints are detector output (integer coordinates): the leaner instantiation applies
     uint8_t *desc;             // 32 bytes per keypoint slot
 };
 cudaError_t launch_brief(const BriefArgs &args, cudaStream_t stream);
