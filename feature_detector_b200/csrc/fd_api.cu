@@ -966,6 +966,7 @@ fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, i
     a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
     a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
     a.cand_capacity = cap;
+    a.work_counter = static_cast<uint32_t *>(ctx->flags.ptr) + 3;   // flags[3]: zeroed above
     FD_CUDA(ctx, launch_nn_heatmap(a, ctx->sm_count, ctx->stream));
     ++ctx->launches;
 

@@ -182,6 +182,7 @@ struct NnHeatmapArgs {
     uint64_t *cand_keys;       // high word ~ordered(response), low word ~((row << 16) | col): equal responses rank the later pixel first
     uint32_t *cand_counts;
     uint32_t cand_capacity;
+    uint32_t *work_counter;    // next run of rows to hand out, zero on entry
 };
 cudaError_t launch_nn_heatmap(const NnHeatmapArgs &args, int sm_count, cudaStream_t stream);
 struct NnDescriptorArgs {

@@ -18,6 +18,7 @@ namespace fdb {
 namespace {
 
 constexpr int NN_STEPS = 2;                 // 128-column steps per pass over a row: 256 columns, one float4 per lane per step
+constexpr int NN_CHUNK_ROWS = 16;            // rows per work item
 constexpr int NN_STAGE = 128 * NN_STEPS;    // candidate keys staged per warp between slot reservations: one pass always fits
 
 // One warp per run of consecutive valid rows (the invalid boundary rows are never read).  Per pass the warp issues all its
@@ -34,17 +35,12 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
     const int valid_rows = p.rows - 2 * b;
     if (valid_rows <= 0 || p.cols - 2 * b <= 0) return;
     const int64_t total_rows = int64_t(p.n_frames) * valid_rows;
-    const int64_t n_warps = int64_t(gridDim.x) * (blockDim.x >> 5);
-    const int64_t per_warp = (total_rows + n_warps - 1) / n_warps;
-    const int64_t first = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * per_warp;
-    const int64_t last = min(first + per_warp, total_rows);
-    if (first >= last) return;
     const int64_t map_px = int64_t(p.rows) * p.cols;
     const bool vec = (p.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(p.heatmap) % 16 == 0);
     const int col_lo = b, col_hi = p.cols - b;   // valid columns: col_lo <= col < col_hi
     if (lane == 0) *fill = 0u;
     __syncwarp();
-    int frame = int(first / valid_rows), row = b + int(first - int64_t(frame) * valid_rows);
+    int frame = 0, row = 0;
     uint32_t staged = 0u;   // keys in the stage (warp-uniform copy of *fill)
     auto flush = [&]() {
         __syncwarp();
@@ -61,6 +57,17 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
             staged = 0u;
         }
     };
+    // runs of NN_CHUNK_ROWS consecutive valid rows are handed out by a global counter (zeroed by the host): the cost of a run
+    // follows its candidate count, so a fixed partition leaves a tail
+    for (;;) {
+    uint32_t chunk = 0u;
+    if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const int64_t first = int64_t(chunk) * NN_CHUNK_ROWS;
+    if (first >= total_rows) break;
+    const int64_t last = min(first + NN_CHUNK_ROWS, total_rows);
+    frame = int(first / valid_rows);
+    row = b + int(first - int64_t(frame) * valid_rows);
     for (int64_t it = first; it < last; ++it) {
         const float *rp = p.heatmap + int64_t(frame) * map_px + int64_t(row) * p.cols;
         for (int base = 0; base < p.cols; base += 128 * NN_STEPS) {
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
             ++frame;
         }
     }
-    flush();
+    flush();   // the stage never carries keys across runs (the next run may belong to another frame)
+    }
 }
 
 __global__ void __launch_bounds__(256) nn_descriptor_kernel(const NnDescriptorArgs p) {
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(256) nn_descriptor_kernel(const NnDescriptorAr
 
 cudaError_t launch_nn_heatmap(const NnHeatmapArgs &args, int sm_count, cudaStream_t stream) {
     const int64_t rows = int64_t(args.n_frames) * std::max(args.rows - 2 * args.invalid_boundary, 0);
-    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, int64_t(8) * sm_count)));   // 8 CTAs of 8 warps per SM, at most one row per warp
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((rows + 127) / 128, int64_t(8) * sm_count)));   // 8 CTAs of 8 warps per SM, at most one 16-row run per warp
     nn_heatmap_kernel<<<grid, 256, 0, stream>>>(args);
     return cudaGetLastError();
 }
