@@ -307,8 +307,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "fdb::fast_sparse_kernel (fd_fast_sparse.cu; thr 10 leaves s_min >= 7, so the sparse form runs)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": round(per_launch * 1e6, 2),
-                "note": "1 B/px kernel: instruction-issue bound (77 % issue slots busy, ALU pipe the fullest), see DESIGN.md section 4 and "
-                        "profiles/r1_fast_sparse_brief_ncu_summary.txt; traffic = dram bytes per launch from that ncu capture"}
+                "note": "1 B/px kernel: instruction-issue bound (80 % issue slots busy, ALU pipe the fullest), see DESIGN.md section 4 and "
+                        "profiles/r1_headline_step_ncu_summary.txt; traffic = dram bytes per launch from that ncu capture"}
     prof = os.path.join(ROOT, "profiles", "fast_kernel_traffic.json")
     if os.path.exists(prof):
         try:
