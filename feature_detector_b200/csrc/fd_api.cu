@@ -717,6 +717,7 @@ fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, 
     FD_TRY(check_params(ctx, params));
     if (rows > 65535 || cols > 65535) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frames are limited to 65535 x 65535");
     FD_TRY(reserve(ctx, ctx->flags, 16));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->flags.ptr, 0, 16, ctx->stream));   // the overflow flag of this selection
     if (ctx->have_existing) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "pre-existing features are not supported with external candidates");
     ctx->mask_view = MaskView{};
     ctx->select_frames = n_frames;
