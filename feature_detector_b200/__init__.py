@@ -118,6 +118,7 @@ def load_library():
         "fd_lsd_field": (C.c_int, [vp, C.POINTER(LsdParams), vp, vp, vp, vp]),
         "fd_descriptors_as_float": (C.c_int, [vp, vp]),
         "fd_download_descriptors_float": (C.c_int, [vp, vp, C.c_int]),
+        "fd_upload_floats": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(vp)]),
         "fd_nn_select_from_heatmap": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(NnParams), C.c_int]),
         "fd_nn_sample_descriptors": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
         "fd_nn_download_descriptors": (C.c_int, [vp, vp, C.c_int]),

@@ -12,6 +12,7 @@
 
 #include "descriptor_brief.h"
 #include "feature_line_detector.h"
+#include "nn_feature_point_postprocess.h"
 #include "feature_line_field.h"
 #include "feature_point_fast_detector.h"
 #include "feature_point_harris_detector.h"
@@ -190,6 +191,35 @@ int main(int argc, char **argv) {
                     lines.size(), detector.rectangles().size(), detector.sorted_pixels().size());
         for (size_t i = 0; i < lines.size(); ++i)
             std::printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", double(lines[i][0]), double(lines[i][1]), double(lines[i][2]), double(lines[i][3]));
+        std::printf("]}");
+    }
+    if (argc >= 8) {   // NN post-processing: <heat map f32 file> <descriptor volume f32 file> <channels> <pre-existing features>
+        const int channels = std::atoi(argv[6]), n_pre = std::atoi(argv[7]);
+        auto read_floats = [](const char *path, size_t n, std::vector<float> &v) {
+            v.resize(n);
+            FILE *g = std::fopen(path, "rb");
+            const bool ok = g != nullptr && std::fread(v.data(), 4, n, g) == n;
+            if (g) std::fclose(g);
+            return ok;
+        };
+        std::vector<float> heat, vol;
+        const int mr = rows / 8, mc = cols / 8;
+        if (!read_floats(argv[4], size_t(rows) * cols, heat) || !read_floats(argv[5], size_t(channels) * mr * mc, vol)) {
+            std::fprintf(stderr, "cannot read the NN inputs\n");
+            return 2;
+        }
+        NNFeaturePointPostProcessor post;
+        std::vector<Vec2> features;
+        for (int i = 0; i < n_pre; ++i) features.emplace_back(Vec2(float(20 + 31 * i % (cols - 40)), float(20 + 17 * i % (rows - 40))));
+        const bool ok = post.SelectGoodFeaturesFromHeatMap(heat.data(), rows, cols, features);
+        std::vector<Vec> desc;
+        const bool ok2 = post.ExtractDescriptorsForSelectedFeatures(features, vol.data(), channels, mr, mc, desc);
+        Fnv dh;
+        for (const Vec &d : desc)
+            for (int j = 0; j < int(d.size()); ++j) dh.F32(d(j));
+        std::printf(",\n \"nn\": {\"ok\": %s, \"ok_desc\": %s, \"n_feat\": %zu, \"feat_hash\": \"%s\", \"n_desc\": %zu, \"desc_hash\": \"%s\", \"features\": [",
+                    ok ? "true" : "false", ok2 ? "true" : "false", features.size(), FeatureHash(features).c_str(), desc.size(), Hex(dh.h).c_str());
+        for (size_t i = 0; i < features.size(); ++i) std::printf("%s[%d, %d]", i ? ", " : "", int(features[i].x()), int(features[i].y()));
         std::printf("]}");
     }
     std::printf("}\n");

@@ -77,7 +77,7 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
-    DevBuf nn_desc, nn_user_desc, desc_float, lsd_work;
+    DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2];
     bool have_desc_float = false;
     int nn_channels = 0;
     bool have_nn_desc = false;
@@ -550,7 +550,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1]})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -977,6 +977,15 @@ fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, i
     sel.needed_feature_num = params->max_features;
     ctx->select_frames = n_frames;
     return run_select(ctx, &sel, rows, cols, n_frames, a.cand_keys, a.cand_counts, cap, 0xFFFFFFFFu);
+}
+
+fd_status fd_upload_floats(fd_context *ctx, int slot, const float *host, size_t count, const float **dev) {
+    if (!ctx || !host || !dev || slot < 0 || slot > 1 || count == 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_upload_floats: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(reserve(ctx, ctx->float_slot[slot], count * 4));
+    FD_CUDA(ctx, cudaMemcpyAsync(ctx->float_slot[slot].ptr, host, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = static_cast<const float *>(ctx->float_slot[slot].ptr);
+    return FD_OK;
 }
 
 fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, float *dev_out) {

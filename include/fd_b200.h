@@ -215,6 +215,10 @@ typedef struct fd_nn_params {
     uint32_t max_features;        /* kMaxNumberOfDetectedFeatures, default 240 */
     int32_t reserved;             /* must be 0 */
 } fd_nn_params;
+/* Model outputs that live in HOST memory (a CPU execution provider): copy `count` floats into one of two context-owned device
+ * buffers (slot 0 / 1, e.g. heat map / descriptor volume) and get the device pointer to hand to the calls below.  The copy is
+ * asynchronous on the context's stream when the source is pinned. */
+fd_status fd_upload_floats(fd_context *ctx, int slot, const float *host, size_t count, const float **dev);
 fd_status fd_nn_select_from_heatmap(fd_context *ctx, const float *dev_heatmap, int rows, int cols, int n_frames, const fd_nn_params *params,
                                     int cand_capacity);
 fd_status fd_nn_sample_descriptors(fd_context *ctx, const float *dev_maps, int channels, int map_rows, int map_cols, float *dev_out);

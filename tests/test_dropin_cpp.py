@@ -16,13 +16,26 @@ CPP = os.path.join(ROOT, "feature_detector_b200", "cpp")
 EXE = os.path.join(CPP, "fd_dropin_check")
 
 
+NN_CHANNELS, NN_PRE = 256, 5
+
+
+def _nn_inputs():
+    from feature_detector_b200.synth import synth_descriptor_volume, synth_heatmap
+    return synth_heatmap(752, 480, 7), synth_descriptor_volume(NN_CHANNELS, 60, 94, 7)
+
+
 @pytest.fixture(scope="module")
 def dropin_output(built, image_png, tmp_path_factory):
     r = subprocess.run(["make", "-C", CPP], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
-    raw = tmp_path_factory.mktemp("dropin") / "image_752x480.u8"
+    tmp = tmp_path_factory.mktemp("dropin")
+    raw = tmp / "image_752x480.u8"
     raw.write_bytes(image_png.tobytes())
-    r = subprocess.run([EXE, str(raw), "480", "752"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    heat, vol = _nn_inputs()
+    (tmp / "heat.f32").write_bytes(heat.tobytes())
+    (tmp / "vol.f32").write_bytes(vol.tobytes())
+    r = subprocess.run([EXE, str(raw), "480", "752", str(tmp / "heat.f32"), str(tmp / "vol.f32"), str(NN_CHANNELS), str(NN_PRE)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     return json.loads(r.stdout)
 
@@ -51,6 +64,25 @@ def test_dropin_has_no_cpu_path(dropin_output):
     assert out["fast_demo"]["ok"] is False and out["harris_demo"]["ok"] is False and out["brief_harris10"]["ok"] is False
     assert out["lsd_field"]["ok"] is False and out["fast_demo"]["n_feat"] == 0 and out["lsd_detect"]["ok"] is False
     assert out["null_image_returns"] is False
+    assert out["nn"]["ok"] is False and out["nn"]["n_feat"] == NN_PRE
+
+
+@pytest.mark.gpu
+def test_dropin_nn_postprocessing(dropin_output, checker):
+    """NNFeaturePointPostProcessor (heat map and descriptor volume in host memory, five pre-existing features) against the
+    reference's nn_feature_point_detector.cpp: same features in the same order, same descriptors bit for bit."""
+    heat, vol = _nn_inputs()
+    pre = np.array([[20 + 31 * i % (752 - 40), 20 + 17 * i % (480 - 40)] for i in range(NN_PRE)], np.float32)
+    o = checker.nn_select(heat, 0.1, 3, 15, 240, pre)
+    nn = dropin_output["nn"]
+    assert nn["ok"] is True and nn["ok_desc"] is True
+    assert nn["n_feat"] == len(o["features"]) == nn["n_desc"]
+    assert np.array_equal(np.array(nn["features"], np.float32), o["features"])
+    exp = checker.nn_descriptors(o["features"], vol)
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(exp, "<f4").tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert nn["desc_hash"] == "%016x" % h
 
 
 @pytest.mark.gpu
