@@ -102,7 +102,7 @@ cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, in
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
-constexpr int SELECT_THREADS = 256;        // per-frame CTA when the cell grid fits shared memory
+constexpr int SELECT_THREADS = 512;        // per-frame CTA when the cell grid fits shared memory (256 and 1024 threads measured: slower overall)
 constexpr int SELECT_MAX_THREADS = 1024;   // ... and when it lives in global memory (very fine grids: thousands of cells per round)
 constexpr int SELECT_SORT_SMEM = 1024;    // kept points sorted in shared memory up to this many
 constexpr int SELECT_CELLS_MIN = 65536;   // frames with more candidates than this group them by cell and run the rounds per cell
