@@ -1087,7 +1087,7 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
     a.angle = dev_angle;
     const int n_strips = (fv.cols + 127) / 128;
     int grid;
-    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 3, 16, 2, a.band_rows, a.n_bands, a.n_items, grid);
+    plan_bands(ctx, fv.rows, n_strips, fv.n_frames, LSD_THREADS / 32, 4, 16, 2, a.band_rows, a.n_bands, a.n_items, grid);
     if (params->want_sorted) {
         FD_TRY(reserve(ctx, ctx->lsd_keys, size_t(a.n_items) * a.band_rows * 128 * 8));
         FD_TRY(reserve(ctx, ctx->lsd_item_counts, size_t(a.n_items) * 4));
