@@ -128,6 +128,7 @@ def load_library():
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
         "fd_debug_fast_offset_bits": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), i32p]),
         "fd_debug_run_length_lut": (C.c_int, [u8p]),
+        "fd_debug_check_guards": (C.c_int, [vp, i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -197,6 +198,12 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.fd_launch_count(self._h))
+
+    def check_guards(self) -> int:
+        """Verify the red zones round every context-owned buffer (contexts created under FD_B200_GUARD=1); returns how many were checked."""
+        n = C.c_int32(0)
+        self._ck(self._lib.fd_debug_check_guards(self._h, C.byref(n)))
+        return n.value
 
     # -- frames --------------------------------------------------------------------------------------
     def upload(self, frames):

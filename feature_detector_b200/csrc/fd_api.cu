@@ -19,6 +19,8 @@ using namespace fdb;
 struct DevBuf {
     void *ptr = nullptr;
     size_t bytes = 0;
+    void *raw = nullptr;       // guard mode (FD_B200_GUARD=1): the allocation, red zones included; ptr = raw + GUARD_BYTES
+    const char *name = "";
 };
 
 struct fd_context {
@@ -28,6 +30,8 @@ struct fd_context {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    bool guard = false;                // FD_B200_GUARD=1: every context-owned buffer is exactly as large as asked for and sits between
+    std::vector<DevBuf *> guarded;     // two red zones that fd_debug_check_guards verifies (compute-sanitizer is not always available)
 
     FrameView fv = {};
     bool frames_bound = false;
@@ -110,23 +114,55 @@ fd_status fail(fd_context *ctx, fd_status st, const std::string &msg) {
         if (s__ != FD_OK) return s__;     \
     } while (0)
 
-fd_status reserve(fd_context *ctx, DevBuf &b, size_t bytes) {
-    if (bytes <= b.bytes && b.ptr != nullptr) return FD_OK;
-    if (b.ptr != nullptr) {
-        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        FD_CUDA(ctx, cudaFree(b.ptr));
-        b.ptr = nullptr;
-        b.bytes = 0;
+constexpr size_t GUARD_BYTES = 256;      // keeps ptr as aligned as cudaMalloc's result for every access width the kernels use
+constexpr int GUARD_PATTERN = 0xA5;
+
+// Guard mode: compare the two red zones of one buffer with the pattern (the caller has synchronised the stream).
+fd_status check_red_zones(fd_context *ctx, const DevBuf &b) {
+    if (!b.raw) return FD_OK;
+    uint8_t zone[2 * GUARD_BYTES];
+    const uint8_t *raw = static_cast<const uint8_t *>(b.raw);
+    FD_CUDA(ctx, cudaMemcpy(zone, raw, GUARD_BYTES, cudaMemcpyDeviceToHost));
+    FD_CUDA(ctx, cudaMemcpy(zone + GUARD_BYTES, raw + GUARD_BYTES + b.bytes, GUARD_BYTES, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < 2 * GUARD_BYTES; ++i) {
+        if (zone[i] == uint8_t(GUARD_PATTERN)) continue;
+        const bool front = i < GUARD_BYTES;
+        return fail(ctx, FD_ERR_CUDA, std::string("red zone ") + (front ? "before " : "after ") + b.name + " (" + std::to_string(b.bytes) +
+                                          " bytes) overwritten at byte " + (front ? "-" + std::to_string(GUARD_BYTES - i) : "+" + std::to_string(i - GUARD_BYTES)));
     }
-    if (bytes == 0) bytes = 16;
-    FD_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
-    b.bytes = bytes;
     return FD_OK;
 }
 
+fd_status reserve_named(fd_context *ctx, DevBuf &b, size_t bytes, const char *name) {
+    if (bytes == 0) bytes = 16;
+    // guard mode never reuses a larger buffer: the red zone has to start where this call's bytes end
+    if (b.ptr != nullptr && (ctx->guard ? bytes == b.bytes : bytes <= b.bytes)) return FD_OK;
+    if (b.ptr != nullptr) {
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FD_TRY(check_red_zones(ctx, b));   // a buffer leaves guard mode's books only after its zones were looked at
+        FD_CUDA(ctx, cudaFree(b.raw ? b.raw : b.ptr));
+        b.ptr = b.raw = nullptr;
+        b.bytes = 0;
+    }
+    if (ctx->guard) {
+        FD_CUDA(ctx, cudaMalloc(&b.raw, bytes + 2 * GUARD_BYTES));
+        uint8_t *raw = static_cast<uint8_t *>(b.raw);
+        FD_CUDA(ctx, cudaMemsetAsync(raw, GUARD_PATTERN, GUARD_BYTES, ctx->stream));
+        FD_CUDA(ctx, cudaMemsetAsync(raw + GUARD_BYTES + bytes, GUARD_PATTERN, GUARD_BYTES, ctx->stream));
+        b.ptr = raw + GUARD_BYTES;
+        b.name = name;
+        if (std::find(ctx->guarded.begin(), ctx->guarded.end(), &b) == ctx->guarded.end()) ctx->guarded.push_back(&b);
+    } else {
+        FD_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
+    }
+    b.bytes = bytes;
+    return FD_OK;
+}
+#define reserve(ctx, b, ...) reserve_named(ctx, b, (__VA_ARGS__), #b)
+
 void release(DevBuf &b) {
-    if (b.ptr) cudaFree(b.ptr);
-    b.ptr = nullptr;
+    if (b.ptr) cudaFree(b.raw ? b.raw : b.ptr);
+    b.ptr = b.raw = nullptr;
     b.bytes = 0;
 }
 
@@ -534,6 +570,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
         return FD_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *env = std::getenv("FD_B200_GUARD")) ctx->guard = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
@@ -577,6 +614,20 @@ fd_status fd_sync(fd_context *ctx) {
 }
 
 uint64_t fd_launch_count(const fd_context *ctx) { return ctx ? ctx->launches : 0; }
+
+fd_status fd_debug_check_guards(fd_context *ctx, int32_t *n_checked) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (n_checked) *n_checked = 0;
+    if (!ctx->guard) return fail(ctx, FD_ERR_NOT_READY, "the context was not created with FD_B200_GUARD=1");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (const DevBuf *b : ctx->guarded) {
+        if (!b->raw) continue;
+        FD_TRY(check_red_zones(ctx, *b));
+        if (n_checked) ++*n_checked;
+    }
+    return FD_OK;
+}
 
 fd_status fd_upload_frames(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames) {
     if (!ctx || !host_frames || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_upload_frames: bad argument");
@@ -1099,7 +1150,7 @@ fd_status fd_lsd_field(fd_context *ctx, const fd_lsd_params *params, float *dev_
         }
         FD_CUDA(ctx, cudaMemsetAsync(ctx->lsd_counts.ptr, 0, size_t(fv.n_frames) * 4, ctx->stream));
         const size_t hist_bytes = size_t(fv.n_frames) * LSD_BINS * 4;
-        if (ctx->lsd_hist.bytes < hist_bytes) ctx->lsd_hist_zeroed = 0;
+        if (ctx->lsd_hist.bytes < hist_bytes || (ctx->guard && ctx->lsd_hist.bytes != hist_bytes)) ctx->lsd_hist_zeroed = 0;   // about to be reallocated
         FD_TRY(reserve(ctx, ctx->lsd_hist, hist_bytes));
         FD_TRY(reserve(ctx, ctx->lsd_start, hist_bytes));
         FD_TRY(reserve(ctx, ctx->lsd_bucketed, px * fv.n_frames * 8));

@@ -236,6 +236,13 @@ fd_status fd_debug_fast_offset_bits(uint32_t count, uint32_t *out_bits, int32_t 
 /* The 65536-entry longest-circular-run table the FAST kernel looks scores up in. */
 fd_status fd_debug_run_length_lut(uint8_t *out_65536);
 
+/* Memory-safety check that needs no external tool: a context created while the environment holds FD_B200_GUARD=1 allocates every
+ * context-owned device buffer at exactly the size a call asks for, between two 256-byte red zones.  This call synchronises and
+ * verifies all of them (*n_checked = buffers looked at); a kernel that wrote outside its buffer turns up as FD_ERR_CUDA with the
+ * buffer's name in fd_last_error.  FD_ERR_NOT_READY if the context was created without the variable.  tools/sanitize_paths.py
+ * drives every kernel instantiation under it. */
+fd_status fd_debug_check_guards(fd_context *ctx, int32_t *n_checked);
+
 #ifdef __cplusplus
 }
 #endif
