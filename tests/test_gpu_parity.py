@@ -706,3 +706,51 @@ def test_nn_postprocessing_golden(ctx, torch_cuda):
             assert np.array_equal(desc[:4].view(np.uint32), gold[name + ".desc_first"].view(np.uint32)), name
             assert np.array_equal(desc.astype(np.float64).sum(0), gold[name + ".desc_sum"]), name
     ctx.set_existing_features([])
+
+
+# ---- races show up as run-to-run differences: the same batch, repeatedly and under different work distributions ---------------
+@pytest.mark.gpu
+def test_results_do_not_depend_on_scheduling(monkeypatch):
+    """Work items are handed out by global counters and candidates are appended with atomics, so the ORDER inside the candidate
+    slots varies from run to run; everything a caller can see (sorted candidates, keypoints, descriptors, LSD maps and seed order)
+    must not.  Three repeats per context, and contexts whose bands are cut differently (FD_B200_ITEMS_PER_WARP 1 / 8 / 37)."""
+    from feature_detector_b200.synth import synth
+    frames = np.stack([synth(333, 217, i) for i in range(12)])
+    big = np.stack([synth(752, 480, 100 + i) for i in range(4)])
+
+    def snapshot(c):
+        out = []
+        for batch in (frames, big):
+            c.upload(batch)
+            for prm in (fd.DetectParams(fd.FAST, 10.0, 20, 200, fast_n=9), fd.DetectParams(fd.FAST, 10.0, 20, 200, fast_n=12),
+                        fd.DetectParams(fd.FAST, 0.1, 15, 100, fast_n=12), fd.DetectParams(fd.HARRIS, 30.0, 20, 200),
+                        fd.DetectParams(fd.SHI_TOMAS, 40.0, 20, 300)):
+                c.detect(prm)
+                c.describe_selected(fd.BriefParams(256, 8))
+                n = int(prm.needed_feature_num)
+                kp, cnt = c.keypoints(n)
+                desc = c.descriptors(n)
+                out.append(cnt.copy())
+                out.append(c.candidate_counts())
+                for f in range(len(batch)):
+                    out.append(kp[f, :cnt[f]].copy())
+                    out.append(desc[f, :cnt[f]].copy())
+                out.append(_cand_table(c, 0))
+            c.lsd_field(fd.LsdParams(20.0, 1))
+            for f in (0, len(batch) - 1):
+                g = c.lsd_download(f)
+                out += [g["norm"], g["angle"], g["sorted_idx"]]
+        return out
+
+    def same(a, b):
+        return len(a) == len(b) and all(x.dtype == y.dtype and x.shape == y.shape and x.tobytes() == y.tobytes() for x, y in zip(a, b))
+
+    base = None
+    for items in ("8", "1", "37"):
+        monkeypatch.setenv("FD_B200_ITEMS_PER_WARP", items)
+        with fd.Context(0) as c:
+            for rep in range(3):
+                snap = snapshot(c)
+                if base is None:
+                    base = snap
+                assert same(base, snap), (items, rep)
