@@ -453,6 +453,26 @@ def main():
             "hbm_frac": round(n_nn * px * 4 * steps2 / s_nn / 1e9 / peak, 4), "bytes_per_px": 4.0}
         del heat, vol
 
+        # ---- the one collective of the batch path: the optional gather of the result slots ----
+        if world > 1 or os.environ.get("FD_BENCH_GATHER") == "1":
+            try:
+                from feature_detector_b200 import sharding
+                ctx.bind_device(d_frames.data_ptr(), H, W, n)
+                device_step()
+                ctx.sync()
+                slots = sharding.device_results(ctx, n, dev, True)     # torch views of the context's device buffers
+
+                def gather_step():
+                    for t in slots:
+                        sharding.gather_frame_slots(t, world * n, rank, world)
+                s_g = timed(gather_step, 10, 2)
+                per_rank = n * NEEDED * (16 + 32) + n * 4
+                extras["keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)"] = {
+                    "ms_per_gather": round(s_g / 10 * 1e3, 3), "bytes_per_rank": per_rank,
+                    "gbytes_s_received_per_rank": round(per_rank * (world - 1) * 10 / s_g / 1e9, 2)}
+            except Exception as e:   # reported, never fatal: the gather is not part of the metric
+                extras["keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)"] = {"error": repr(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": "Mpixel/s (FAST+NMS+BRIEF, 752x480)", "value": round(value, 2), "unit": "Mpixel/s",
