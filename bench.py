@@ -465,13 +465,19 @@ def main():
                 def gather_step():
                     for t in slots:
                         sharding.gather_frame_slots(t, world * n, rank, world)
-                s_g = timed(gather_step, 10, 2)
+
+                def gather_packed_step():
+                    sharding.gather_frame_records(list(slots), world * n, rank, world)
                 per_rank = n * NEEDED * (16 + 32) + n * 4
-                extras["keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)"] = {
-                    "ms_per_gather": round(s_g / 10 * 1e3, 3), "bytes_per_rank": per_rank,
-                    "gbytes_s_received_per_rank": round(per_rank * (world - 1) * 10 / s_g / 1e9, 2)}
+                name = "keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)"
+                s_g = timed(gather_step, 10, 2)
+                extras[name] = {"ms_per_gather": round(s_g / 10 * 1e3, 3), "bytes_per_rank": per_rank,
+                                "gbytes_s_received_per_rank": round(per_rank * (world - 1) * 10 / s_g / 1e9, 2)}
+                s_p = timed(gather_packed_step, 10, 2)
+                extras[name]["packed_one_all_gather"] = {"ms_per_gather": round(s_p / 10 * 1e3, 3),
+                                                         "gbytes_s_received_per_rank": round(per_rank * (world - 1) * 10 / s_p / 1e9, 2)}
             except Exception as e:   # reported, never fatal: the gather is not part of the metric
-                extras["keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)"] = {"error": repr(e)[:300]}
+                extras.setdefault("keypoint gather (all_gather of keypoint, descriptor and count slots over NCCL)", {})["error"] = repr(e)[:300]
 
     if rank == 0:
         line = {

@@ -3,11 +3,12 @@
 Frames are independent -- nothing crosses frames once each has its own candidate and keypoint slots -- so the batch is cut
 into contiguous blocks, one per rank, and the data path needs no collective at all.  The only exchange is the OPTIONAL final
 gather of the results, which are fixed-capacity slots per frame (``kp_capacity`` x 16-byte keypoints, ``kp_capacity`` x 32-byte
-descriptors, one count), hence one ``all_gather`` per array over equal-sized blocks (the last ranks' blocks are padded by at
-most one frame).  Plumbing only:
+descriptors, one count), hence one ``all_gather`` over equal-sized blocks (the last ranks' blocks are padded by at most one
+frame).  Plumbing only:
 
 * ``frame_range``            -- the block of frames a rank owns;
-* ``gather_frame_slots``     -- all_gather of per-frame slot arrays (torch tensors: CUDA over NCCL, CPU over gloo in the tests);
+* ``gather_frame_slots``     -- all_gather of one per-frame slot array (torch tensors: CUDA over NCCL, CPU over gloo in the tests);
+* ``gather_frame_records``   -- several slot arrays packed into one byte record per frame: one all_gather for all of them;
 * ``detect_sharded``         -- upload / bind this rank's block, fd_detect (+ fd_describe_selected), optional gather straight
                                 from the context's device buffers (no host round trip before the collective).
 """
@@ -48,6 +49,43 @@ def gather_frame_slots(local, n_frames: int, rank: int, world: int, dst: int | N
         a, b = frame_range(n_frames, r, world)
         parts.append(out[r][:b - a])
     return torch.cat(parts)
+
+
+def gather_frame_records(tensors, n_frames: int, rank: int, world: int, dst: int | None = None, group=None):
+    """Several per-frame slot arrays at once (keypoints, counts, descriptors ...): the arrays of one frame are packed into one
+    byte record, so the whole exchange is ONE all_gather (``all_gather_into_tensor``: no per-rank output copies) whatever the
+    number of arrays.  ``tensors``: torch tensors with this rank's block of frames as first dimension.  Returns the list of
+    (n_frames, ...) tensors in frame order -- on every rank, or only on ``dst`` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = frame_range(n_frames, rank, world)
+    n_local = hi - lo
+    assert all(t.shape[0] == n_local for t in tensors), ([tuple(t.shape) for t in tensors], lo, hi)
+    if world == 1:
+        return list(tensors)
+    widths = [int(np.prod(t.shape[1:], dtype=np.int64)) * t.element_size() for t in tensors]   # bytes per frame of each array
+    longest = max(frame_range(n_frames, 0, world)[1], 1)
+    record = torch.zeros((longest, sum(widths)), dtype=torch.uint8, device=tensors[0].device)
+    col = 0
+    for t, w in zip(tensors, widths):
+        if n_local:
+            record[:n_local, col:col + w] = t.contiguous().reshape(n_local, -1).view(torch.uint8)
+        col += w
+    out = torch.empty((world * longest, sum(widths)), dtype=torch.uint8, device=record.device)
+    dist.all_gather_into_tensor(out, record, group=group)
+    if dst is not None and rank != dst:
+        return None
+    blocks = []
+    for r in range(world):
+        a, b = frame_range(n_frames, r, world)
+        blocks.append(out[r * longest:r * longest + (b - a)])
+    rows = torch.cat(blocks)                                            # (n_frames, record bytes), frame order
+    result, col = [], 0
+    for t, w in zip(tensors, widths):
+        part = rows[:, col:col + w].contiguous()
+        result.append(part.view(t.dtype).reshape((n_frames,) + tuple(t.shape[1:])))
+        col += w
+    return result
 
 
 class _DeviceArray:
@@ -107,11 +145,11 @@ def detect_sharded(ctx, frames, n_frames: int, rank: int, world: int, detect, br
         cnt = torch.zeros((0,), dtype=torch.int32, device=device)
         desc = torch.zeros((0, cap, 32), dtype=torch.uint8, device=device) if brief is not None else None
     if gather:
-        kp = gather_frame_slots(kp, n_frames, rank, world, dst, group)
-        cnt = gather_frame_slots(cnt, n_frames, rank, world, dst, group)
-        desc = gather_frame_slots(desc, n_frames, rank, world, dst, group) if desc is not None else None
-        if kp is None:
+        got = gather_frame_records([kp, cnt] + ([desc] if desc is not None else []), n_frames, rank, world, dst, group)
+        if got is None:
             return None
+        kp, cnt = got[0], got[1]
+        desc = got[2] if desc is not None else None
     out_kp = np.ascontiguousarray(kp.cpu().numpy()).view(np.float32)
     rec = np.zeros(out_kp.shape[:2], KEYPOINT_DTYPE)
     rec["x"], rec["y"], rec["response"] = out_kp[..., 0], out_kp[..., 1], out_kp[..., 2]

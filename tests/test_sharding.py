@@ -58,12 +58,17 @@ def _gloo_worker(rank, world, port, ret):
         got = [sharding.gather_frame_slots(torch.from_numpy(a), N_FRAMES, rank, world, dst=0) for a in (kp, cnt, desc)]
         everywhere = sharding.gather_frame_slots(torch.from_numpy(cnt), N_FRAMES, rank, world)   # no dst: every rank gets it
         ret[f"all{rank}"] = everywhere.numpy().tolist()
+        # the packed form: all three arrays in one all_gather
+        packed = sharding.gather_frame_records([torch.from_numpy(a) for a in (kp, cnt, desc)], N_FRAMES, rank, world, dst=0)
+        packed_all = sharding.gather_frame_records([torch.from_numpy(cnt)], N_FRAMES, rank, world)
+        ret[f"packed_all{rank}"] = packed_all[0].numpy().tolist()
         if rank == 0:
             want = _port_slots([synth(W, H, i) for i in range(N_FRAMES)])
             ret["same"] = all(np.array_equal(g.numpy(), w) for g, w in zip(got, want))
+            ret["same_packed"] = all(g.dtype == torch.from_numpy(w).dtype and np.array_equal(g.numpy(), w) for g, w in zip(packed, want))
             ret["counts"] = want[1].tolist()
         else:
-            ret[f"none{rank}"] = all(g is None for g in got)
+            ret[f"none{rank}"] = all(g is None for g in got) and packed is None
     finally:
         dist.destroy_process_group()
 
@@ -77,6 +82,7 @@ def test_gathered_slots_equal_the_unsharded_batch_over_gloo(world, built):
         assert ret["same"] and sum(ret["counts"]) > 0, dict(ret)
         assert all(ret[f"none{r}"] for r in range(1, world))
         assert all(ret[f"all{r}"] == ret["counts"] for r in range(world))
+        assert ret["same_packed"] and all(ret[f"packed_all{r}"] == ret["counts"] for r in range(world))
 
 
 def _nccl_worker(rank, world, port, ret):
