@@ -30,6 +30,16 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
             if (MODE == 11) asm volatile("vimnmx_placeholder_%=: max.u16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
             if (MODE == 12) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
             if (MODE == 13) { asm volatile("{.reg .pred p; setp.gt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(a[i]) : "r"(b), "r"(c)); }
+            // integer dot products and 16-bit pairs (candidates for the corner kernels' exact window sums), conversions
+            if (MODE == 14) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+            if (MODE == 15) { if (i & 1) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+            if (MODE == 16) { if (i & 1) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); else asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+            if (MODE == 17) { if (i & 1) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); else asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+            if (MODE == 18) a[i] = __vadd2(a[i], b);
+            if (MODE == 19) { if (i & 1) asm volatile("mul.rn.f32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)); else asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a[i]) : "r"(c)); }
+            if (MODE == 20) asm volatile("cvt.rn.f32.u32 %0, %0;" : "+r"(a[i]));
+            if (MODE == 21) asm volatile("cvt.rzi.u32.f32 %0, %0;" : "+r"(a[i]));
+            if (MODE == 22) asm volatile("dp2a.lo.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
         }
     }
     uint32_t s = 0;
@@ -74,6 +84,15 @@ int main() {
     run<11>("VIMNMX.U16x2", 1, out, p.multiProcessorCount, mhz);
     run<12>("FFMA", 1, out, p.multiProcessorCount, mhz);
     run<13>("ISETP+SEL", 2, out, p.multiProcessorCount, mhz);
+    run<14>("IDP.4A", 1, out, p.multiProcessorCount, mhz);
+    run<15>("IDP.4A+LOP3 (1:1)", 1, out, p.multiProcessorCount, mhz);
+    run<16>("IDP.4A+HFMA2 (1:1)", 1, out, p.multiProcessorCount, mhz);
+    run<17>("IDP.4A+FFMA (1:1)", 1, out, p.multiProcessorCount, mhz);
+    run<18>("VIADD.16x2", 1, out, p.multiProcessorCount, mhz);
+    run<19>("FMUL+FADD (1:1)", 1, out, p.multiProcessorCount, mhz);
+    run<20>("I2F.U32", 1, out, p.multiProcessorCount, mhz);
+    run<21>("F2I.U32", 1, out, p.multiProcessorCount, mhz);
+    run<22>("IDP.2A", 1, out, p.multiProcessorCount, mhz);
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
