@@ -14,18 +14,18 @@ constexpr int kNeighbourRow[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 constexpr int kNeighbourCol[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
 }  // namespace
 
-FeatureLineDetector::FeatureLineDetector() { sorted_pixels_.reserve(10000); }
+FeatureLineDetector::FeatureLineDetector() { host_.seeds.reserve(10000); }
 
 bool FeatureLineDetector::ComputeLineLevelAngleMap(const GrayImage &image) {
     field_.options().kMinValidGradientNorm = options_.kMinValidGradientNorm;
     if (!field_.Compute(image)) return false;                       // kernel 5 + seed order on the GPU
-    field_.FillPixelParams(pixels_, sorted_pixels_);                // what .cpp:56-97 leaves behind
+    field_.FillPixelParams(host_.grid, host_.seeds);                // what .cpp:56-97 leaves behind
     if (options_.kHostLibmAngles) {
         // same expression as .cpp:76-85 for the valid pixels only (a few percent of the frame)
         const int32_t cols = image.cols();
         const uint8_t *data = image.data();
-        const PixelParam *first = pixels_.data(), *last = pixels_.data() + pixels_.size();
-        for (PixelParam *px : sorted_pixels_) {
+        const PixelParam *first = host_.grid.data(), *last = host_.grid.data() + host_.grid.size();
+        for (PixelParam *px : host_.seeds) {
             if (px < first || px >= last) continue;   // an entry left over from a call on a differently sized frame (.cpp:7-10 never clears)
             const int32_t r = px->row, c = px->col;
             const int32_t ad = int32_t(data[(r + 1) * cols + c + 1]) - int32_t(data[r * cols + c]);
@@ -50,8 +50,8 @@ bool FeatureLineDetector::DetectGoodFeatures(const GrayImage &image, const uint3
     if (!ComputeLineLevelAngleMap(image)) return false;
 
     RegionParam region;
-    rectangles_.clear();
-    for (PixelParam *seed : sorted_pixels_) {                                           // .cpp:27-46
+    host_.segments.clear();
+    for (PixelParam *seed : host_.seeds) {                                           // .cpp:27-46
         if (!seed->is_valid || seed->is_used) continue;
         GrowRegion(*seed, region);
         if (region.pixels.size() < min_region_size) {
@@ -62,11 +62,11 @@ bool FeatureLineDetector::DetectGoodFeatures(const GrayImage &image, const uint3
         if (rect.length < options_.kMinValidLineLengthInPixel || rect.inlier_ratio < options_.kMaxToleranceInlierRation) continue;
         rect.start_point += Vec2::Constant(0.5f);                                       // .cpp:43-44
         rect.end_point += Vec2::Constant(0.5f);
-        rectangles_.emplace_back(rect);
+        host_.segments.emplace_back(rect);
     }
 
     features.clear();
-    for (const RectangleParam &rect : rectangles_)
+    for (const RectangleParam &rect : host_.segments)
         features.emplace_back(Vec4(rect.start_point.x(), rect.start_point.y(), rect.end_point.x(), rect.end_point.y()));
     return true;
 }
@@ -74,25 +74,25 @@ bool FeatureLineDetector::DetectGoodFeatures(const GrayImage &image, const uint3
 void FeatureLineDetector::Enqueue(PixelParam &neighbour) {                              // .cpp:156-161
     if (neighbour.is_occupied || neighbour.is_used || !neighbour.is_valid) return;
     neighbour.is_occupied = true;
-    frontier_.PushBack(&neighbour);
+    host_.frontier.PushBack(&neighbour);
 }
 
 void FeatureLineDetector::GrowRegion(PixelParam &seed, RegionParam &region) {           // .cpp:99-154
-    frontier_.Clear();
-    touched_.Clear();
-    touched_.PushBack(&seed);
+    host_.frontier.Clear();
+    host_.touched.Clear();
+    host_.touched.PushBack(&seed);
     seed.is_occupied = true;
 
     region.pixels.clear();
     region.angle = seed.line_level_angle;
     float sum_dx = std::cos(seed.line_level_angle);
     float sum_dy = std::sin(seed.line_level_angle);
-    for (int k = 0; k < 8; ++k) Enqueue(pixels_(seed.row + kNeighbourRow[k], seed.col + kNeighbourCol[k]));
+    for (int k = 0; k < 8; ++k) Enqueue(host_.grid(seed.row + kNeighbourRow[k], seed.col + kNeighbourCol[k]));
 
-    while (!frontier_.Empty()) {
-        PixelParam *px = frontier_.Front();
-        frontier_.PopFront();
-        touched_.PushBack(px);
+    while (!host_.frontier.Empty()) {
+        PixelParam *px = host_.frontier.Front();
+        host_.frontier.PopFront();
+        host_.touched.PushBack(px);
         const float residual = Utility::AngleDiffInRad(region.angle, px->line_level_angle);
         if (std::fabs(residual) > options_.kMinToleranceAngleResidualInRad) continue;
         sum_dx += std::cos(px->line_level_angle);
@@ -100,11 +100,11 @@ void FeatureLineDetector::GrowRegion(PixelParam &seed, RegionParam &region) {   
         region.angle = std::atan2(sum_dy, sum_dx);
         region.pixels.emplace_back(px);
         px->is_used = true;
-        for (int k = 0; k < 8; ++k) Enqueue(pixels_(px->row + kNeighbourRow[k], px->col + kNeighbourCol[k]));
+        for (int k = 0; k < 8; ++k) Enqueue(host_.grid(px->row + kNeighbourRow[k], px->col + kNeighbourCol[k]));
     }
-    while (!touched_.Empty()) {
-        touched_.Front()->is_occupied = false;
-        touched_.PopFront();
+    while (!host_.touched.Empty()) {
+        host_.touched.Front()->is_occupied = false;
+        host_.touched.PopFront();
     }
 }
 
