@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: per captured kernel the headline metrics, stall reasons and (optionally) hot source lines."""
-import csv, subprocess, sys, io, collections
+import csv, subprocess, sys, io, collections, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)   # piping into head must not end in a traceback
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
