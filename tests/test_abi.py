@@ -99,3 +99,32 @@ def test_sparsify_host_logic(port, vectors):
         assert np.array_equal(fd.sparsify(f, rows, cols, 1, 2, s0, gr, gc), port.sparsify(f, rows, cols, 1, 2, s0, gr, gc))
     # size mismatch -> all ones first (feature_point_detector.cpp:29-31)
     assert np.array_equal(fd.sparsify(f, 480, 752, 1, 2, None), port.sparsify(f, 480, 752, 1, 2, np.zeros(0, np.uint8)))
+
+
+def test_sparse_fast_filter_is_conservative():
+    """The facts the sparse FAST kernel's phase A rests on (fd_fast_sparse.cu header), checked exhaustively on the CPU:
+    every ring mask whose longest circular run is >= 4 contains a compass position (ring 0, 4, 8, 12), every one with a run >= 8
+    contains a vertical AND a horizontal compass position, every one with a run >= 12 passes the pre-check's closed form or
+    contains 3 compass positions; and the packed-byte threshold test `(|a - b| & mask) != 0` with mask = bits at or above the largest
+    power of two <= diff + 1 never misses a pixel with |a - b| > diff (exact when diff + 1 is a power of two, e.g. the default 15)."""
+    lib = fd.load_library()
+    lut = np.zeros(65536, np.uint8)
+    assert lib.fd_debug_run_length_lut(lut.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+    m = np.arange(65536, dtype=np.uint32)
+    compass = [(m >> i) & 1 for i in (0, 4, 8, 12)]           # top, right, bottom, left
+    any_c = (compass[0] | compass[1] | compass[2] | compass[3]).astype(bool)
+    adj_c = ((compass[0] | compass[2]) & (compass[1] | compass[3])).astype(bool)
+    three = (compass[0] + compass[1] + compass[2] + compass[3]) >= 3
+    assert any_c[lut >= 4].all() and not any_c[lut >= 3].all()          # 4 is the smallest run length the ANY test may serve
+    assert adj_c[lut >= 8].all() and not adj_c[lut >= 7].all()          # 8 the smallest for ADJ (a run of 7 can hold one compass point)
+    assert three[lut >= 12].all() and not three[lut >= 11].all()        # the reference's kN >= 12 pre-check idea (fast.cpp:20-42)
+    for diff in range(256):
+        shift = 0
+        while (2 << shift) <= diff + 1:
+            shift += 1                                                   # 2^shift = largest power of two <= diff + 1 (fd_api.cu)
+        mask = (0xFF << shift) & 0xFF
+        a = np.arange(256)
+        flagged = (a & mask) != 0
+        assert flagged[a > diff].all(), diff                             # conservative: nothing above diff slips through
+        if (diff + 1) & diff == 0:
+            assert not flagged[a <= diff].any(), diff                    # exact for diff + 1 a power of two
