@@ -57,11 +57,15 @@ void RunDetector(const char *label, Detector &det, const GrayImage &image, float
     int64_t mask_zeros = 0;
     const MatInt &mask = det.mask();
     for (int64_t i = 0; i < mask.size(); ++i) mask_zeros += (mask.data()[i] == 0);
+    Fnv mh;   // row-major walk, whatever the matrix's storage order
+    for (int32_t r = 0; r < mask.rows(); ++r)
+        for (int32_t c = 0; c < mask.cols(); ++c) mh.I32(int32_t(mask(r, c)));
     std::printf("%s\"%s\": {\"ok\": %s, \"name\": \"%s\", \"n_pre\": %zu, \"n_feat\": %zu, \"feat_hash\": \"%s\", \"n_cand\": %zu, "
-                "\"first\": [%d, %d], \"mask_zeros\": %lld, \"mask_rows\": %d, \"mask_cols\": %d, \"top_response\": %.9g}",
+                "\"first\": [%d, %d], \"mask_zeros\": %lld, \"mask_rows\": %d, \"mask_cols\": %d, \"mask_hash\": \"%s\", \"top_response\": %.9g}",
                 first ? "" : ",\n ", label, ok ? "true" : "false", det.DetectorTypeName().c_str(), n_pre, features.size(), FeatureHash(features).c_str(),
                 det.candidates().size(), features.size() > n_pre ? int(features[n_pre].x()) : -1, features.size() > n_pre ? int(features[n_pre].y()) : -1,
-                static_cast<long long>(mask_zeros), mask.rows(), mask.cols(), det.candidates().empty() ? 0.0 : double(det.candidates()[0].first));
+                static_cast<long long>(mask_zeros), int(mask.rows()), int(mask.cols()), Hex(mh.h).c_str(),
+                det.candidates().empty() ? 0.0 : double(det.candidates()[0].first));
 }
 
 struct PixelParam {  // field-for-field the reference's FeatureLineDetector::PixelParam (feature_line_detector.h:14-22)

@@ -28,16 +28,50 @@ def _nn_inputs():
 def dropin_output(built, image_png, tmp_path_factory):
     r = subprocess.run(["make", "-C", CPP], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
-    tmp = tmp_path_factory.mktemp("dropin")
+    return _run_check(EXE, image_png, tmp_path_factory.mktemp("dropin"))
+
+
+def _run_check(exe, image_png, tmp):
     raw = tmp / "image_752x480.u8"
     raw.write_bytes(image_png.tobytes())
     heat, vol = _nn_inputs()
     (tmp / "heat.f32").write_bytes(heat.tobytes())
     (tmp / "vol.f32").write_bytes(vol.tobytes())
-    r = subprocess.run([EXE, str(raw), "480", "752", str(tmp / "heat.f32"), str(tmp / "vol.f32"), str(NN_CHANNELS), str(NN_PRE)],
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    r = subprocess.run([exe, str(raw), "480", "752", str(tmp / "heat.f32"), str(tmp / "vol.f32"), str(NN_CHANNELS), str(NN_PRE)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     return json.loads(r.stdout)
+
+
+@pytest.fixture(scope="module")
+def dropin_output_host_glue(built, image_png, tmp_path_factory):
+    """fd_dropin_check and the drop-in classes linked against tests/hoststage/fake_fd_abi.cpp (the C ABI with the CPU oracle behind it,
+    test infrastructure) instead of libfd_b200.so: the host glue of feature_detector_b200/cpp runs without a GPU."""
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "fd_dropin_check_host_glue")
+    srcs = [os.path.join(CPP, f) for f in ("fd_dropin_check.cpp", "feature_point_detector.cpp", "descriptor_brief.cpp", "feature_line_field.cpp",
+                                           "line_segments_host.cpp", "nn_feature_point_postprocess.cpp")]
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-Wall", "-I" + CPP, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "compat", "slam_utility"),
+           "-o", exe] + srcs + [os.path.join(ROOT, "tests", "hoststage", "fake_fd_abi.cpp"), "-L" + os.path.join(ROOT, "oracle"), "-lfd_oracle",
+                                "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-4000:]
+    return _run_check(exe, image_png, tmp_path_factory.mktemp("dropin_host_glue"))
+
+
+def _feature_hash(features):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(np.asarray(features).astype("<i4")).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def _mask_hash(mask):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(mask, "<i4").tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
 
 
 def test_dropin_headers_keep_the_reference_surface():
@@ -71,6 +105,15 @@ def test_dropin_has_no_cpu_path(dropin_output):
 def test_dropin_nn_postprocessing(dropin_output, checker):
     """NNFeaturePointPostProcessor (heat map and descriptor volume in host memory, five pre-existing features) against the
     reference's nn_feature_point_detector.cpp: same features in the same order, same descriptors bit for bit."""
+    _check_nn(dropin_output, checker)
+
+
+def test_dropin_host_glue_nn_postprocessing(dropin_output_host_glue, checker):
+    """The same expectations for the host glue alone (CPU; oracle behind the C ABI)."""
+    _check_nn(dropin_output_host_glue, checker)
+
+
+def _check_nn(dropin_output, checker):
     heat, vol = _nn_inputs()
     pre = np.array([[20 + 31 * i % (752 - 40), 20 + 17 * i % (480 - 40)] for i in range(NN_PRE)], np.float32)
     o = checker.nn_select(heat, 0.1, 3, 15, 240, pre)
@@ -86,8 +129,17 @@ def test_dropin_nn_postprocessing(dropin_output, checker):
 
 
 @pytest.mark.gpu
-def test_dropin_replays_reference_demos(dropin_output, kat, image_png):
-    out = dropin_output
+def test_dropin_replays_reference_demos(dropin_output, kat, image_png, checker):
+    _check_demos(dropin_output, kat, image_png, checker)
+
+
+def test_dropin_host_glue_replays_reference_demos(dropin_output_host_glue, kat, image_png, checker):
+    """fd_dropin_check through the host glue alone (CPU; oracle behind the C ABI): marshalling, the in/out features contract, the
+    lazily rebuilt mask() / candidates(), bit unpacking, PixelParam filling and the LSD host stage against the same golden answers."""
+    _check_demos(dropin_output_host_glue, kat, image_png, checker)
+
+
+def _check_demos(out, kat, image_png, checker):
     gold = {(c["detector"], c["thr"]): c for c in kat["cases"] if c["frame"] == "image" and "thr" in c}
     for label, key, name in (("fast_demo", ("fast", 10.0), "Fast"), ("harris_demo", ("harris", 30.0), "Harris"), ("shi_demo", ("shi", 40.0), "Shi-Tomas"),
                              ("fast9_demo", ("fast9", 10.0), "Fast"), ("harris_default_reused", ("harris", 0.1), "Harris")):
@@ -104,6 +156,18 @@ def test_dropin_replays_reference_demos(dropin_output, kat, image_png):
     assert pre["first"] == [520, 201]
     # mask(): FAST demo found 84 < 200 features, so every feature cleared its clipped 41x41 square
     assert 0 < out["fast_demo"]["mask_zeros"] <= 84 * 41 * 41
+    # mask() after a call is the reference's mask_, exactly: all ones minus the squares of the pre-existing features and of
+    # every accepted feature except the one that reached the count (feature_point_detector.cpp:67-69)
+    from oracle.bindings import FAST, HARRIS, SHI_TOMAS
+    pre81 = np.array([[15 * i, 15 * j] for i in range(1, 10) for j in range(1, 10)], np.float32)
+    for label, kind, thr, d, fast_n, pre_feats in (("fast_demo", FAST, 10.0, 20, 12, None), ("harris_demo", HARRIS, 30.0, 20, 0, None),
+                                                   ("shi_demo", SHI_TOMAS, 40.0, 20, 0, None), ("fast9_demo", FAST, 10.0, 20, 9, None),
+                                                   ("harris_preseeded81", HARRIS, 30.0, 20, 0, pre81), ("harris_default_reused", HARRIS, 0.1, 15, 0, None)):
+        o = checker.detect(kind, image_png, thr, d, 200, fast_n=fast_n, pre=pre_feats, want_mask=True, want_candidates=False)
+        if len(o["features"]) == out[label]["n_feat"] and np.array_equal(out[label].get("first", [-1, -1]), o["features"][len(pre_feats) if pre_feats is not None else 0].astype(int)):
+            assert out[label]["mask_zeros"] == int((o["mask"] == 0).sum()), label
+            if out[label]["feat_hash"] == _feature_hash(o["features"]):   # identical feature lists (no tie resolved differently): identical masks
+                assert out[label]["mask_hash"] == _mask_hash(o["mask"]), label
     assert out["null_image_returns"] is False
 
     b = out["brief_harris10"]
