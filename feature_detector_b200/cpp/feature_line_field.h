@@ -60,7 +60,7 @@ public:
             pixels(i, pc - 1).col = pc - 1;
         }
         for (int32_t i = 0; i < pc; ++i) {                                        // .cpp:64-68 (the (0, 1) index is the reference's)
-            pixels(0, 1).col = i;
+            if (pc > 1) pixels(0, 1).col = i;                                     // two-column images: the reference writes out of bounds here
             pixels(pr - 1, i).col = i;
             pixels(pr - 1, i).row = pr - 1;
         }

@@ -103,3 +103,47 @@ def test_host_stage_edge_cases(hoststage):
     assert rc == 0 and info["lines"] == 1
     x0, y0, x1, y1 = lines[0]
     assert abs(x0 - 94) < 1 and abs(x1 - 94) < 1 and abs(abs(y1 - y0) - 156) < 3
+
+
+def test_host_glue_is_clean_under_asan_and_ubsan(built, image_png, tmp_path):
+    """SURVEY.md section 5 (the reference builds without sanitizers): the drop-in classes' host code under -fsanitize=address,undefined,
+    with the oracle behind the C ABI -- the whole fd_dropin_check replay, and the line detector on frames down to 2 x 2 pixels (a
+    two-column frame makes the reference itself write out of bounds in feature_line_detector.cpp:64-68; the drop-in guards that line)."""
+    cpp = os.path.join(ROOT, "feature_detector_b200", "cpp")
+    os.makedirs(BUILD, exist_ok=True)
+    flags = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I" + cpp, "-I" + os.path.join(ROOT, "include"),
+             "-I" + os.path.join(ROOT, "compat", "slam_utility")]
+    link = ["-L" + os.path.join(ROOT, "oracle"), "-lfd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
+    hs = os.path.join(BUILD, "hoststage_check_asan")
+    full = os.path.join(BUILD, "fd_dropin_check_asan")
+    probe = subprocess.run(flags + ["-x", "c++", "-", "-o", os.path.join(BUILD, "asan_probe")], input="int main(){return 0;}", text=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if probe.returncode != 0:
+        pytest.skip("this toolchain has no sanitizer runtime")
+    for exe, srcs in ((hs, [os.path.join(ROOT, "tests", "hoststage", "hoststage_check.cpp"), os.path.join(cpp, "line_segments_host.cpp")]),
+                      (full, [os.path.join(cpp, f) for f in ("fd_dropin_check.cpp", "feature_point_detector.cpp", "descriptor_brief.cpp", "feature_line_field.cpp",
+                                                             "line_segments_host.cpp", "nn_feature_point_postprocess.cpp")] +
+                             [os.path.join(ROOT, "tests", "hoststage", "fake_fd_abi.cpp")])):
+        r = subprocess.run(flags + ["-o", exe] + srcs + link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+
+    def clean(cmd):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+        assert r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr, (cmd, r.stderr[-3000:])
+        return r.stdout
+
+    rng = np.random.default_rng(0)
+    from feature_detector_b200.synth import synth, synth_descriptor_volume, synth_heatmap
+    for shape in [(2, 2), (2, 5), (5, 2), (3, 3), (4, 4), (6, 2), (2, 9), (7, 7), (60, 80), (217, 333)]:
+        frame = rng.integers(0, 256, shape, dtype=np.uint8) if shape[0] < 50 else synth(shape[1], shape[0], 3)
+        path = tmp_path / "frame.u8"
+        frame.tofile(path)
+        out = clean([hs, str(path), str(shape[0]), str(shape[1]), "50", "5.0"])
+        assert out.startswith("ok 1")
+    raw = tmp_path / "image.u8"
+    raw.write_bytes(image_png.tobytes())
+    synth_heatmap(752, 480, 7).tofile(tmp_path / "heat.f32")
+    synth_descriptor_volume(256, 60, 94, 7).tofile(tmp_path / "vol.f32")
+    out = clean([full, str(raw), "480", "752", str(tmp_path / "heat.f32"), str(tmp_path / "vol.f32"), "256", "5"])
+    assert '"lsd_detect": {"ok": true, "n_lines": 40' in out
