@@ -202,3 +202,51 @@ def test_brief_vec_overload_port_equals_reference(port, ref, image_png):
         ok_b, b = port.brief_vec(image_png, kp, length)
         assert ok_a and ok_b and np.array_equal(a, b)
         assert np.array_equal(a > 0, ref.brief(image_png, kp, length)[1].astype(bool)) and set(np.unique(a)) <= {-1.0, 1.0}
+
+
+def test_port_equals_reference_on_random_small_inputs(port, ref):
+    """Fuzz of the C restatement against the reference compiled in place: random images from 1 x 1 pixels up (noise, binary, flat, step +
+    noise), all three detectors, thresholds from -1 to 1e9, distances 0..100, needed 0..1000, pre-existing features, BRIEF at keypoints
+    inside and outside the frame, the LSD maps.  Candidates, responses and masks must agree bit for bit; feature lists too unless two
+    candidates tie (the reference's std::sort leaves their order open).  (The reference's line detector is skipped below 3 x 3: on a
+    two-column frame it writes out of bounds, feature_line_detector.cpp:64-68.)"""
+    from oracle.bindings import FAST, HARRIS, SHI_TOMAS
+    rng = np.random.default_rng(20261018)
+    for it in range(800):
+        rows, cols = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        mode = int(rng.integers(0, 4))
+        if mode == 0:
+            img = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+        elif mode == 1:
+            img = (rng.integers(0, 2, (rows, cols)) * 255).astype(np.uint8)
+        elif mode == 2:
+            img = np.full((rows, cols), int(rng.integers(0, 256)), np.uint8)
+        else:
+            img = np.zeros((rows, cols), np.uint8)
+            img[rows // 3:, cols // 4:] = 200
+            img = (img + rng.integers(0, 6, (rows, cols))).astype(np.uint8)
+        kind = (FAST, HARRIS, SHI_TOMAS)[int(rng.integers(0, 3))]
+        thr = float(rng.choice([0.0, 0.1, 5.0, 10.0, 30.0, 1e9, -1.0]))
+        d, needed, fast_n = int(rng.choice([0, 1, 5, 15, 20, 100])), int(rng.choice([0, 1, 3, 50, 1000])), int(rng.choice([9, 12]))
+        n_pre = int(rng.choice([0, 0, 3]))
+        pre = np.stack([rng.uniform(0, cols, n_pre), rng.uniform(0, rows, n_pre)], 1).astype(np.float32) if n_pre else None
+        case = (it, rows, cols, kind, thr, d, needed, fast_n, n_pre)
+        a = port.detect(kind, img, thr, d, needed, fast_n=fast_n, pre=pre, want_mask=True, want_response=(kind != FAST))
+        b = ref.detect(kind, img, thr, d, needed, fast_n=fast_n, pre=pre, want_mask=True, want_response=(kind != FAST))
+        assert a["ok"] == b["ok"] and a["n_cand"] == b["n_cand"], case
+        if kind != FAST:
+            assert np.array_equal(a["response"].view(np.uint32), b["response"].view(np.uint32)), case
+        ka, kb = np.lexsort((a["cand_xy"][:, 0], a["cand_xy"][:, 1])), np.lexsort((b["cand_xy"][:, 0], b["cand_xy"][:, 1]))
+        assert np.array_equal(a["cand_xy"][ka], b["cand_xy"][kb]) and np.array_equal(a["cand_resp"][ka].view(np.uint32), b["cand_resp"][kb].view(np.uint32)), case
+        if np.array_equal(a["features"], b["features"]):
+            assert np.array_equal(a["mask"], b["mask"]), case
+        else:
+            assert len(np.unique(a["cand_resp"])) < len(a["cand_resp"]), case      # only a tie may reorder the walk
+        if rows >= 3 and cols >= 3:
+            la, lb = port.lsd_map(img), ref.lsd_map(img)
+            assert np.array_equal(la["norm"].view(np.uint32), lb["norm"].view(np.uint32)) and np.array_equal(la["valid"], lb["valid"]), case
+            assert np.array_equal(la["angle"].view(np.uint32), lb["angle"].view(np.uint32)), case
+        if rows > 40 and cols > 40:
+            kp = np.stack([rng.uniform(-2, cols + 2, 6), rng.uniform(-2, rows + 2, 6)], 1).astype(np.float32)
+            ba, bb = port.brief(img, kp, 256, 8), ref.brief(img, kp, 256, 8)
+            assert ba[0] == bb[0] and np.array_equal(ba[1], bb[1]), case
