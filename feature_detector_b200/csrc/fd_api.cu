@@ -598,6 +598,7 @@ const char *fd_last_error(const fd_context *ctx) { return ctx ? ctx->err.c_str()
 
 fd_status fd_set_stream(fd_context *ctx, void *cuda_stream) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     return FD_OK;
@@ -777,6 +778,7 @@ fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, 
 
 fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts) {
     if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
     FD_CUDA(ctx, cudaMemcpyAsync(host_counts, ctx->counts.ptr, size_t(ctx->fv.n_frames) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -785,6 +787,7 @@ fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts) {
 
 fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out) {
     if (!ctx || !n_out) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_candidates) return fail(ctx, FD_ERR_NOT_READY, "no candidates computed");
     if (frame < 0 || frame >= ctx->fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame out of range");
     FD_TRY(check_overflow(ctx));
@@ -810,6 +813,7 @@ fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_
 
 fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *host_counts, int kp_capacity) {
     if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
     FD_TRY(check_overflow(ctx));
     const int nf = ctx->select_frames;
@@ -922,6 +926,7 @@ fd_status fd_describe_points(fd_context *ctx, const fd_brief_params *params, con
 
 fd_status fd_download_descriptors(fd_context *ctx, uint8_t *host_desc, int kp_capacity) {
     if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
     const int nf = ctx->fv.n_frames;
     const int w = std::min(kp_capacity, ctx->desc_capacity);
@@ -950,6 +955,7 @@ fd_status fd_descriptors_as_float(fd_context *ctx, float *dev_out) {
 
 fd_status fd_download_descriptors_float(fd_context *ctx, float *host_desc, int kp_capacity) {
     if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_desc_float) return fail(ctx, FD_ERR_NOT_READY, "fd_descriptors_as_float has not written to the context's buffer");
     const size_t row = size_t(ctx->desc_length) * 4;
     const int w = std::min(kp_capacity, ctx->desc_capacity);
@@ -1104,6 +1110,7 @@ fd_status fd_nn_sample_descriptors_at(fd_context *ctx, const float *dev_maps, in
 
 fd_status fd_nn_download_descriptors(fd_context *ctx, float *host_desc, int kp_capacity) {
     if (!ctx || !host_desc) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_nn_desc) return fail(ctx, FD_ERR_NOT_READY, "fd_nn_sample_descriptors has not written to the context's buffer");
     const size_t row = size_t(ctx->nn_channels) * 4;
     const int w = std::min(kp_capacity, ctx->kp_capacity);
@@ -1198,6 +1205,7 @@ fd_status fd_lsd_device_outputs(fd_context *ctx, const float **dev_norm, const f
 fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *host_angle, int32_t *host_sorted_idx, int64_t sorted_capacity,
                           int32_t *host_n_valid) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_lsd) return fail(ctx, FD_ERR_NOT_READY, "fd_lsd_field has not run");
     const FrameView &fv = ctx->fv;
     if (frame < 0 || frame >= fv.n_frames) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "frame out of range");
