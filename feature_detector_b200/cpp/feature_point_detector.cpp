@@ -2,6 +2,7 @@
 #include "feature_point_detector.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "fd_b200.h"
@@ -151,7 +152,9 @@ void FeaturePointDetector::SparsifyFeatures(const std::vector<Vec2> &features, c
     const float row_step = float(image_rows / (grid_rows - 1)), col_step = float(image_cols / (grid_cols - 1));
     for (size_t i = 0; i < features.size(); ++i) {
         if (before[i] != status_need_filter) continue;
-        const int32_t row = int32_t(features[i].y() / row_step), col = int32_t(features[i].x() / col_step);
+        const float qr = features[i].y() / row_step, qc = features[i].x() / col_step;   // a step of 0 (image smaller than the grid): outside
+        if (!(std::fabs(qr) < 2.0e9f && std::fabs(qc) < 2.0e9f)) continue;
+        const int32_t row = int32_t(qr), col = int32_t(qc);
         if (row >= 0 && row < grid_rows && col >= 0 && col < grid_cols) mask_(row, col) = 0;
     }
 }

@@ -851,8 +851,12 @@ fd_status fd_sparsify(const float *host_xy, int n, int image_rows, int image_col
     const float row_step = float(row_div), col_step = float(col_div);
     std::vector<uint8_t> free_cell(size_t(grid_rows) * grid_cols, 1);                          // :36
     for (int i = 0; i < n; ++i) {
-        const int row = int(host_xy[2 * i + 1] / row_step);                                    // :38
-        const int col = int(host_xy[2 * i] / col_step);                                        // :39
+        // An image smaller than the grid makes a step 0 and the quotient infinite or NaN; the reference's float -> int cast of that is
+        // undefined (INT_MIN on x86, i.e. outside the grid).  Same outcome here, without the undefined cast.
+        const float qr = host_xy[2 * i + 1] / row_step, qc = host_xy[2 * i] / col_step;
+        const bool in_range = std::fabs(qr) < 2.0e9f && std::fabs(qc) < 2.0e9f;                // false for NaN too
+        const int row = in_range ? int(qr) : -1;                                               // :38
+        const int col = in_range ? int(qc) : -1;                                               // :39
         if (row < 0 || row > grid_rows - 1 || col < 0 || col > grid_cols - 1) {                // :41-44
             status[i] = status_after_filter;
             continue;

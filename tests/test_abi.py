@@ -93,7 +93,7 @@ def test_sparsify_host_logic(port, vectors):
     st = fd.sparsify(vectors["sparsify.features"], 480, 752, 1, 2, vectors["sparsify.status_in"])
     assert np.array_equal(st, vectors["sparsify.status_out"])
     rng = np.random.default_rng(5)
-    for rows, cols, gr, gc in [(480, 752, 12, 12), (720, 1280, 8, 10), (100, 100, 3, 4)]:
+    for rows, cols, gr, gc in [(480, 752, 12, 12), (720, 1280, 8, 10), (100, 100, 3, 4), (5, 5, 12, 12), (480, 9, 12, 12)]:   # the last two: a step of 0
         f = np.stack([rng.uniform(-30, cols + 30, 300), rng.uniform(-30, rows + 30, 300)], 1).astype(np.float32)
         s0 = rng.integers(0, 3, 300).astype(np.uint8)
         assert np.array_equal(fd.sparsify(f, rows, cols, 1, 2, s0, gr, gc), port.sparsify(f, rows, cols, 1, 2, s0, gr, gc))
