@@ -141,6 +141,10 @@ def test_host_glue_is_clean_under_asan_and_ubsan(built, image_png, tmp_path):
         frame.tofile(path)
         out = clean([hs, str(path), str(shape[0]), str(shape[1]), "50", "5.0"])
         assert out.startswith("ok 1")
+    for shape in [(1, 1), (2, 2), (3, 9), (7, 7), (10, 200), (41, 41), (64, 40)]:      # the whole replay (detectors, BRIEF, line detector) on small frames
+        path = tmp_path / "small.u8"
+        rng.integers(0, 256, shape, dtype=np.uint8).tofile(path)
+        clean([full, str(path), str(shape[0]), str(shape[1])])
     raw = tmp_path / "image.u8"
     raw.write_bytes(image_png.tobytes())
     synth_heatmap(752, 480, 7).tofile(tmp_path / "heat.f32")
