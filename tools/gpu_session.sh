@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# One-liners for a GPU box (run under `gpurun -- 'tools/gpu_session.sh <what> [...]'`); everything lands in gpurun_out/.
+# Measured costs of round 1 (warm box): tests ~75 s, bench ~25 s, bench --no-extras ~15 s, guard ~8 s, pipes ~2 s.
+#   tests        python -m pytest tests -m gpu -x -q            (the round-end suite)
+#   fuzz         the gated fuzz of the C ABI against the checker on frames from 1 x 1 pixels up (not yet run on a GPU)
+#   guard        every kernel instantiation with red zones round every buffer (tools/sanitize_paths.py)
+#   bench        python bench.py  -> gpurun_out/bench_<tag>.json          (tag = $2, default "run")
+#   bench-n N    torchrun bench.py --gpus N (use with gpurun --gpus N)    (tag = $3)
+#   nccl         the multi-GPU tests (sharded batch + gather, row-tiled 4K frame); use with gpurun --gpus 2
+#   launches     ncu launch list of the headline step (gpu__time_duration.sum, --clock-control none)
+#   ncu          one --set full capture of the headline step's three kernels -> gpurun_out/prof_<tag>.ncu-rep, then read it HERE with
+#                tools/ncu_summary.py / tools/ncu_regions.py / tools/ncu_hotspots.py
+#   pipes        tools/microbench/pipes (issue rates of the instruction mixes the kernels are made of)
+set -u
+mkdir -p gpurun_out
+what=${1:-tests}
+case "$what" in
+  tests)    python -m pytest tests -m gpu -x -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_gpu.log ;;
+  fuzz)     FD_GPU_FUZZ=1 python -m pytest tests/test_gpu_fuzz.py -m gpu -x -q > gpurun_out/pytest_fuzz.log 2>&1; echo "rc=$?"; tail -25 gpurun_out/pytest_fuzz.log ;;
+  guard)    python tools/sanitize_paths.py > gpurun_out/sanitize_guard.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sanitize_guard.log ;;
+  bench)    tag=${2:-run}; python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "rc=$?"; tail -c 600 gpurun_out/bench_$tag.json ;;
+  bench-n)  n=${2:-2}; tag=${3:-run}; python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 \
+              bench.py --gpus "$n" > gpurun_out/bench_${n}gpu_$tag.json 2> gpurun_out/bench_${n}gpu_$tag.err; echo "rc=$?"; tail -c 900 gpurun_out/bench_${n}gpu_$tag.json ;;
+  nccl)     python -m pytest tests/test_sharding.py tests/test_tiling.py -m gpu -x -q -k nccl > gpurun_out/pytest_nccl.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_nccl.log ;;
+  launches) python bench.py --steps 2 --warmup 3 --no-extras > /dev/null 2>&1 && \
+            ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+              python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/ncu_launches.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_launches.log ;;
+  ncu)      tag=${2:-run}; python bench.py --steps 1 --warmup 3 --no-extras > /dev/null 2>&1 && \
+            ncu --set full --clock-control none --import-source on -k regex:'fast_sparse_kernel|select_kernel|brief_kernel' -c 3 -f -o gpurun_out/prof_$tag \
+              python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_$tag.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_$tag.log ;;
+  pipes)    make -s -C tools/microbench pipes 2>/dev/null || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/pipes tools/microbench/pipes.cu; \
+            tools/microbench/pipes > gpurun_out/pipes.txt 2>&1; echo "rc=$?"; cat gpurun_out/pipes.txt ;;
+  *)        echo "unknown: $what"; sed -n 2,16p "$0"; exit 2 ;;
+esac
