@@ -53,6 +53,9 @@ public:
     template <typename PixelMatrix, typename PixelPtrVector>
     void FillPixelParams(PixelMatrix &pixels, PixelPtrVector &sorted) const {
         const int32_t pr = rows_ - 1, pc = cols_ - 1;
+        // Deliberate deviation: a frame of another size reallocates the matrix, and the pointers the reference would keep in
+        // sorted_pixels_ dangle from then on (undefined behaviour there, so no parity to keep) -- they are dropped here.
+        if (pixels.rows() != pr || pixels.cols() != pc) sorted.clear();
         pixels.resize(pr, pc);                                                    // .cpp:58
         for (int32_t i = 0; i < pr; ++i) {                                        // .cpp:59-63
             pixels(i, 0).row = i;

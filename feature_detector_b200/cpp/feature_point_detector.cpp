@@ -75,13 +75,23 @@ bool FeaturePointDetector::DetectGoodFeaturesBatch(const uint8_t *frames, int32_
     p.harris_alpha = HarrisAlpha();
     p.fast_n = FastN();
     p.fast_min_pixel_diff = FastMinPixelDiff();
-    if (fd_detect(ctx_, &p, 0) != FD_OK) return Fail("fd_detect");
-
-    // At most max(needed - existing, 1) new features per frame (push first, test afterwards: :67-68).
-    const int cap = int(std::max<uint32_t>(needed_feature_num, 1u));
+    // At most max(needed - existing, 1) new features per frame (push first, test afterwards: :67-68), and never more than the
+    // frame has pixels or the library's keypoint slots hold (needed = UINT32_MAX is a legitimate "all of them").
+    const int cap = int(std::min<uint64_t>({uint64_t(std::max<uint32_t>(needed_feature_num, 1u)), uint64_t(rows) * uint64_t(cols), uint64_t(1) << 20}));
     std::vector<fd_keypoint> kp(size_t(n_frames) * cap);
     std::vector<int32_t> counts(size_t(n_frames), 0);
-    if (fd_download_keypoints(ctx_, kp.data(), counts.data(), cap) != FD_OK) return Fail("fd_download_keypoints");
+    // Candidate slots: one per pixel can never overflow, but costs 24 B per pixel per frame of scratch on the device.  A batch
+    // therefore starts with a quarter of that (a corner detector fills ~7 % on textured frames) and runs again with full slots if a
+    // frame overflows (FAST at the reference's default threshold makes nearly every pixel a candidate).
+    const int64_t px = int64_t(rows) * cols;
+    int cand_capacity = (n_frames > 1 && px / 4 >= (1 << 16)) ? int(px / 4) : 0;
+    for (;;) {
+        if (fd_detect(ctx_, &p, cand_capacity) != FD_OK) return Fail("fd_detect");
+        const fd_status st = fd_download_keypoints(ctx_, kp.data(), counts.data(), cap);
+        if (st == FD_OK) break;
+        if (st != FD_ERR_CAPACITY || cand_capacity == 0) return Fail("fd_download_keypoints");
+        cand_capacity = 0;
+    }
 
     // bookkeeping for the lazily rebuilt mask() of frame 0 (the single-frame call's frame)
     mask_rows_ = rows;

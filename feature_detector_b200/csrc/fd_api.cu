@@ -51,6 +51,7 @@ struct fd_context {
     int kp_capacity = 0;
     bool have_keypoints = false;
     int select_frames = 0;     // frames the last selection covered (the bound frames, or external candidates)
+    bool kp_of_bound_frames = false;   // the keypoints were selected on the frames that are bound now (not on row tiles, gathered keys or heat maps)
 
     DevBuf user_kp, user_counts;
     int user_capacity = 0;
@@ -404,7 +405,9 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
     if (p->kind == FD_FAST) {
         if (ctx->score_map) FD_CUDA(ctx, cudaMemsetAsync(ctx->score_map, 0, size_t(fv.n_frames) * px, ctx->stream));
         if (fv.rows >= 7 && fv.cols >= 7) {
-            const uint32_t interior = uint32_t(tile.full_rows - 6) * uint32_t(fv.cols - 6);
+            const uint64_t interior64 = uint64_t(tile.full_rows - 6) * uint64_t(fv.cols - 6);
+            if (interior64 > 0xFFFFFFF0ull) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "FAST: the frame has more interior pixels than the 32-bit pixel index of the running offset holds");
+            const uint32_t interior = uint32_t(interior64);
             FD_TRY(ensure_fast_tables(ctx, interior));
             FastArgs a = {};
             a.fv = fv;
@@ -518,7 +521,8 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.cells_x = (fv.cols + cell - 1) / cell;
     a.cells_y = (fv.rows + cell - 1) / cell;
     const size_t cell_bytes = select_cell_bytes(a.cells_x, a.cells_y);   // the grid carries a one-cell empty border
-    a.cell_magic = uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
+    // ceil(2^32 / cell) does not fit 32 bits for cells of one pixel (min distance 0): 0 stands for the identity there
+    a.cell_magic = cell == 1 ? 0u : uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
     a.cells_in_smem = cell_bytes <= 48 * 1024;
     if (!a.cells_in_smem) {
         FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
@@ -538,6 +542,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
     ctx->select_frames = fv.n_frames;
+    ctx->kp_of_bound_frames = false;   // fd_detect sets it after its own selection
     return FD_OK;
 }
 
@@ -711,8 +716,10 @@ fd_status fd_detect(fd_context *ctx, const fd_detect_params *params, int cand_ca
     FD_CUDA(ctx, cudaSetDevice(ctx->device));
     FD_TRY(run_candidates(ctx, params, cand_capacity));
     if (ctx->tiled) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_detect on a row tile: gather the tiles' candidates and call fd_select_candidates");
-    return run_select(ctx, params, ctx->fv.rows, ctx->fv.cols, ctx->fv.n_frames, static_cast<uint64_t *>(ctx->keys.ptr),
-                      static_cast<const uint32_t *>(ctx->counts.ptr), ctx->cand_capacity);
+    FD_TRY(run_select(ctx, params, ctx->fv.rows, ctx->fv.cols, ctx->fv.n_frames, static_cast<uint64_t *>(ctx->keys.ptr),
+                      static_cast<const uint32_t *>(ctx->counts.ptr), ctx->cand_capacity));
+    ctx->kp_of_bound_frames = true;
+    return FD_OK;
 }
 
 fd_status fd_set_tile(fd_context *ctx, int row_offset, int own_first_row, int own_row_count, int full_rows) {
@@ -900,6 +907,9 @@ fd_status fd_describe_selected(fd_context *ctx, const fd_brief_params *params) {
     FD_CUDA(ctx, cudaSetDevice(ctx->device));
     FD_TRY(require_frames(ctx));
     if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
+    // keypoints selected from gathered row-tile candidates or a heat map live in another frame count / coordinate frame than the bound frames
+    if (!ctx->kp_of_bound_frames || ctx->select_frames != ctx->fv.n_frames)
+        return fail(ctx, FD_ERR_NOT_READY, "the selected keypoints do not belong to the bound frames: bind the full frames and use fd_describe_points");
     ctx->desc_from_user = false;
     return run_brief(ctx, params, static_cast<const float4 *>(ctx->kp.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), ctx->kp_capacity);
 }

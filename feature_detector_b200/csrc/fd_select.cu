@@ -166,13 +166,14 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     // during the rounds the same storage lists the cells that must rescan their candidates (never more cells than candidates)
     uint32_t *work = reinterpret_cast<uint32_t *>(admitted_keys);
     uint64_t *kept = p.kept_keys + int64_t(frame) * p.kept_capacity;
-    const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536
+    const uint32_t cell_magic = p.cell_magic;  // ceil(2^32 / (d+1)): exact quotient for coordinates < 65536; 0 = cells of one pixel (d = 0)
     const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
     const uint32_t *mb = p.mask.bits ? p.mask.bits + int64_t(frame) * p.rows * p.mask.words_per_row : nullptr;
     const uint32_t xy_xor = p.xy_xor;
     auto key_xy = [&](uint64_t key) { return uint32_t(key) ^ xy_xor; };   // (row << 16) | col
     auto cell_of = [&](uint32_t xy) {
-        const int cx = int(__umulhi(xy & 0xFFFFu, cell_magic)), cy = int(__umulhi(xy >> 16, cell_magic));
+        const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
+        const int cx = int(cell_magic ? __umulhi(x, cell_magic) : x), cy = int(cell_magic ? __umulhi(y, cell_magic) : y);
         return (cy + 1) * pitch + cx + 1;
     };
 

@@ -1,16 +1,13 @@
 """Fuzz of the CUDA path against the checker on random small frames -- the generator of
-tests/test_oracle.py::test_port_equals_reference_on_random_small_inputs pointed at the C ABI.
-
-Written after round 1's GPU budget was spent, so it has not run on a GPU yet: it is gated behind FD_GPU_FUZZ=1 rather than left to fail
-(or pass) unseen in the round-end suite.  First thing to enable next round."""
-import os
-
+tests/test_oracle.py::test_port_equals_reference_on_random_small_inputs pointed at the C ABI: frames from 1 x 1 pixels up, extreme
+thresholds, min distances 0 .. 100 (0 = cells of one pixel in the selection kernel), pre-existing features, LSD maps, BRIEF at
+out-of-range keypoints."""
 import numpy as np
 import pytest
 
 import feature_detector_b200 as fd
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("FD_GPU_FUZZ") != "1", reason="not yet run on a GPU; set FD_GPU_FUZZ=1")]
+pytestmark = pytest.mark.gpu
 
 
 def test_cuda_path_equals_checker_on_random_small_frames(checker):

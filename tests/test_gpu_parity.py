@@ -608,6 +608,17 @@ def test_selection_per_cell_equals_per_candidate(checker):
                 o = checker.detect(FAST, frames[f], 0.1, 15, 200, fast_n=12)
                 feats = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
                 assert np.array_equal(feats, o["features"]), f
+            # min distance 0 and 1: cells of one and two pixels (the cell index is the pixel itself at 0), both forms against the checker
+            for d in (0, 1):
+                for c in (per_cell, per_cand):
+                    c.upload(frames)
+                    c.set_existing_features([])
+                    c.detect(fd.DetectParams(fd.FAST, 5.0, d, 400, fast_n=9), 0)
+                    kp, cnt = c.keypoints(400)
+                    for f in range(len(frames)):
+                        o = checker.detect(FAST, frames[f], 5.0, d, 400, fast_n=9)
+                        feats = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
+                        assert np.array_equal(feats, o["features"]), (d, f)
     finally:
         per_cell.close()
         per_cand.close()
