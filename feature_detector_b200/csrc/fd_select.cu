@@ -30,14 +30,11 @@
 //
 // sort_kernel: bitonic sort of each frame's keys (shared memory when they fit).  Not on the detection path;
 // used when the caller asks for the sorted candidate list on the device.
-#include "fd_kernels.cuh"
+#include "fd_select_common.cuh"
 
 namespace fdb {
 
 namespace {
-
-constexpr uint32_t kEmptyCell = 0xFFFFFFFFu;
-constexpr uint64_t kDeadKey = 0xFFFFFFFFFFFFFFFFull;
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(uint64_t *keys, const uint32_t *counts, int64_t slot, uint32_t capacity,
                                                             int smem_capacity, uint32_t *overflow_flag) {
@@ -57,80 +54,6 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(uint64_t *keys, cons
     }
 }
 
-// The cell grid carries a one-cell border (pitch = cells_x + 2, cell (cx, cy) at (cy + 1) * pitch + cx + 1) that stays
-// empty, so the 3x3 neighbourhood of any cell can be read without bounds tests.
-//
-// Is (x, y) within Chebyshev distance d of a point kept in the 3x3 cells around cell index c?  A kept point is stored as
-// (y << 16) | x; "both coordinates inside [x-d, x+d] x [y-d, y+d]" is one packed clamp: clamp(q, lo, hi) == q on 16-bit
-// halves (VIMNMX.U16x2).  The upper bounds stop at 65534, which no coordinate of a frame of at most 65535 columns / rows
-// exceeds, so the empty marker 0xFFFFFFFF is never inside the box.
-__device__ __forceinline__ bool near_kept(const uint32_t *cells, int pitch, int c, int x, int y, int d) {
-    const uint32_t lo = (uint32_t(max(y - d, 0)) << 16) | uint32_t(max(x - d, 0));
-    const uint32_t hi = (uint32_t(min(y + d, 65534)) << 16) | uint32_t(min(x + d, 65534));
-    bool hit = false;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const uint32_t q = cells[c + dy * pitch + dx];
-            hit |= (__vminu2(__vmaxu2(q, lo), hi) == q);
-        }
-    }
-    return hit;
-}
-
-// Best (smallest) key posted to the 8 cells around cell index c.
-__device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin, int pitch, int c) {
-    uint64_t best = kDeadKey;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (dx == 0 && dy == 0) continue;
-            best = min(best, uint64_t(cmin[c + dy * pitch + dx]));
-        }
-    }
-    return best;
-}
-
-// Unordered append of this thread's surviving candidate key to a list (warp-aggregated counter bump).
-__device__ __forceinline__ void list_push(bool keep, uint64_t value, uint64_t *list, uint32_t *counter) {
-    const uint32_t m = __ballot_sync(__activemask(), keep);
-    if (m == 0u) return;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0u;
-    if (lane_id() == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(__activemask(), base, leader);
-    if (keep) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
-}
-
-// Exclusive prefix sum of one value per thread over the whole CTA (up to 1024 threads).
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums) {
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane_id() >= o) incl += u;
-    }
-    if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const uint32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane_id() >= o) wi += u;
-        }
-        warp_sums[threadIdx.x] = wi - w;
-    }
-    __syncthreads();
-    const uint32_t r = warp_sums[threadIdx.x >> 5] + incl - v;
-    __syncthreads();   // warp_sums is free again
-    return r;
-}
-
-constexpr int SELECT_HIST_BITS = 11;   // rank-prefix histogram over the top key bits: sign, exponent, two mantissa bits
 
 // BY_CELLS picks the form of the rounds; a launch of one form leaves the frames of the other alone (the candidate counts live
 // on the device, so the host launches both forms whenever the capacity admits the per-cell one).
@@ -158,6 +81,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     const uint32_t count = p.cand_counts[frame];
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
+    if (n < p.lean_limit) return;   // fd_select_lean.cu takes the frame
     if ((n > p.cells_min) != BY_CELLS) return;
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
     // binned: the admitted candidates grouped by cell; admitted: the same keys in arrival order, before grouping

@@ -557,14 +557,17 @@ def test_corner_kernels_agree_with_and_without_masks(ctx):
         stream_ctx.close()
 
 
-# ---- the two forms of the selection rounds (fd_select.cu): per live candidate and per cell -------------------------------
+# ---- the three forms of the selection rounds: event-driven (fd_select_lean.cu, the default), per live candidate and per cell (fd_select.cu) ----
 def _ctx_with_select_threshold(value):
+    """A context that selects with the forms of fd_select.cu only: per cell above `value` candidates, per candidate below."""
     import os
     os.environ["FD_B200_SELECT_CELLS_MIN"] = str(value)
+    os.environ["FD_B200_SELECT_LEAN"] = "0"
     try:
         return fd.Context(0)
     finally:
         del os.environ["FD_B200_SELECT_CELLS_MIN"]
+        del os.environ["FD_B200_SELECT_LEAN"]
 
 
 def test_selection_per_cell_equals_per_candidate(checker):
@@ -572,7 +575,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
     same candidates must give the same keypoints, with and without pre-existing features, for one and for several rank
     batches, fine and coarse cell grids."""
     from feature_detector_b200.synth import synth
-    per_cell, per_cand = _ctx_with_select_threshold(0), _ctx_with_select_threshold(1 << 30)
+    per_cell, per_cand, lean = _ctx_with_select_threshold(0), _ctx_with_select_threshold(1 << 30), fd.Context(0)
     try:
         rng = np.random.default_rng(11)
         batches = [np.stack([synth(320, 200, i) for i in range(6)]),
@@ -586,7 +589,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
             for kind, thr, d, n, fast_n in cases:
                 for with_existing in (False, True):
                     out = []
-                    for c in (per_cell, per_cand):
+                    for c in (per_cell, per_cand, lean):
                         c.upload(frames)
                         if with_existing:
                             c.set_existing_features(existing)
@@ -595,10 +598,11 @@ def test_selection_per_cell_equals_per_candidate(checker):
                         c.detect(fd.DetectParams(kind, thr, d, n, fast_n=fast_n), 0)
                         kp, cnt = c.keypoints(max(n, 1))
                         out.append((kp, cnt))
-                    assert np.array_equal(out[0][1], out[1][1]), (kind, thr, d, n, with_existing)
-                    for f in range(len(frames)):
-                        k = out[0][1][f]
-                        assert np.array_equal(out[0][0][f, :k], out[1][0][f, :k]), (kind, thr, d, n, with_existing, f)
+                    for other in (1, 2):
+                        assert np.array_equal(out[0][1], out[other][1]), (kind, thr, d, n, with_existing, other)
+                        for f in range(len(frames)):
+                            k = out[0][1][f]
+                            assert np.array_equal(out[0][0][f, :k], out[other][0][f, :k]), (kind, thr, d, n, with_existing, f, other)
             # and against the checker for one case per batch (ties are open in the reference's unstable sort)
             per_cell.upload(frames)
             per_cell.set_existing_features([])
@@ -610,7 +614,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
                 assert np.array_equal(feats, o["features"]), f
             # min distance 0 and 1: cells of one and two pixels (the cell index is the pixel itself at 0), both forms against the checker
             for d in (0, 1):
-                for c in (per_cell, per_cand):
+                for c in (per_cell, per_cand, lean):
                     c.upload(frames)
                     c.set_existing_features([])
                     c.detect(fd.DetectParams(fd.FAST, 5.0, d, 400, fast_n=9), 0)
@@ -622,6 +626,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
     finally:
         per_cell.close()
         per_cand.close()
+        lean.close()
 
 
 def test_host_pipeline_equals_single_call(ctx, torch_cuda):
