@@ -126,6 +126,22 @@ def load_library():
                                                   C.POINTER(C.c_float)]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
+        "fd_tiled_create": (C.c_int, [i32p, C.c_int, C.POINTER(vp)]),
+        "fd_tiled_destroy": (C.c_int, [vp]),
+        "fd_tiled_last_error": (C.c_char_p, [vp]),
+        "fd_tiled_upload_frames": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int]),
+        "fd_tiled_scatter_device_frames": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int]),
+        "fd_tiled_tile_info": (C.c_int, [vp, C.c_int, i32p, i32p, i32p, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(vp)]),
+        "fd_tiled_exchange_halos": (C.c_int, [vp]),
+        "fd_tiled_halo_bytes": (C.c_uint64, [vp]),
+        "fd_tiled_compute_candidates": (C.c_int, [vp, C.POINTER(DetectParams), C.c_int]),
+        "fd_tiled_detect": (C.c_int, [vp, C.POINTER(DetectParams), C.c_int]),
+        "fd_tiled_sync": (C.c_int, [vp]),
+        "fd_tiled_candidate_counts": (C.c_int, [vp, i32p]),
+        "fd_tiled_device_candidates": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), i32p]),
+        "fd_tiled_download_candidates": (C.c_int, [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64)]),
+        "fd_tiled_download_keypoints": (C.c_int, [vp, vp, i32p, C.c_int]),
+        "fd_tiled_root_context": (vp, [vp]),
         "fd_debug_fast_offset_bits": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), i32p]),
         "fd_debug_run_length_lut": (C.c_int, [u8p]),
         "fd_debug_check_guards": (C.c_int, [vp, i32p]),
@@ -150,6 +166,93 @@ def sparsify(features_xy, image_rows, image_cols, status_need_filter, status_aft
     if rc != 0:
         raise FdError(rc, "fd_sparsify")
     return st
+
+
+class TiledDetector:
+    """Large frames row-tiled over the GPUs of a box in ONE process (fd_tiled_*, csrc/fd_tiled.cu): tile k of every frame on
+    devices[k] (ordinals may repeat), halo rows by device-to-device peer copies, candidate keys packed on devices[0] by a kernel
+    that reads the peers' slots, selection there.  Results equal Context.detect on the whole frames."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        dev = np.ascontiguousarray(devices, np.int32)
+        rc = self._lib.fd_tiled_create(dev.ctypes.data_as(C.POINTER(C.c_int32)), len(dev), C.byref(self._h))
+        if rc != 0:
+            raise FdError(rc, "fd_tiled_create failed (no CUDA device? there is no CPU fallback)")
+        self.n_tiles = len(dev)
+        self.rows = self.cols = self.n_frames = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FdError(rc, (self._lib.fd_tiled_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._lib.fd_tiled_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, frames: np.ndarray):
+        f = np.ascontiguousarray(frames, np.uint8)
+        if f.ndim == 2:
+            f = f[None]
+        self.n_frames, self.rows, self.cols = f.shape
+        self._ck(self._lib.fd_tiled_upload_frames(self._h, f.ctypes.data_as(C.c_void_p), self.rows, self.cols, self.n_frames))
+
+    def scatter_device(self, dev_ptr: int, rows: int, cols: int, n_frames: int = 1, pitch: int = 0, frame_stride: int = 0):
+        pitch = pitch or cols
+        self.n_frames, self.rows, self.cols = n_frames, rows, cols
+        self._ck(self._lib.fd_tiled_scatter_device_frames(self._h, C.c_void_p(dev_ptr), rows, cols, pitch, frame_stride or pitch * rows, n_frames))
+
+    def tile_info(self, tile: int):
+        dev, first, count = C.c_int32(), C.c_int32(), C.c_int32()
+        ptr, stream = C.c_void_p(), C.c_void_p()
+        pitch, stride = C.c_int64(), C.c_int64()
+        self._ck(self._lib.fd_tiled_tile_info(self._h, tile, C.byref(dev), C.byref(first), C.byref(count), C.byref(ptr), C.byref(pitch), C.byref(stride),
+                                              C.byref(stream)))
+        return {"device": dev.value, "own_first_row": first.value, "own_row_count": count.value, "ptr": ptr.value or 0, "pitch": pitch.value,
+                "frame_stride": stride.value, "stream": stream.value or 0}
+
+    def exchange_halos(self):
+        self._ck(self._lib.fd_tiled_exchange_halos(self._h))
+
+    @property
+    def halo_bytes(self) -> int:
+        return int(self._lib.fd_tiled_halo_bytes(self._h))
+
+    def compute_candidates(self, params: DetectParams, cand_capacity_per_tile: int = 0):
+        self._ck(self._lib.fd_tiled_compute_candidates(self._h, C.byref(params), cand_capacity_per_tile))
+
+    def detect(self, params: DetectParams, cand_capacity_per_tile: int = 0):
+        self._ck(self._lib.fd_tiled_detect(self._h, C.byref(params), cand_capacity_per_tile))
+
+    def sync(self):
+        self._ck(self._lib.fd_tiled_sync(self._h))
+
+    def candidate_counts(self) -> np.ndarray:
+        out = np.zeros(self.n_frames, np.int32)
+        self._ck(self._lib.fd_tiled_candidate_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def candidates(self, frame: int = 0) -> np.ndarray:
+        n = C.c_int64()
+        self._ck(self._lib.fd_tiled_download_candidates(self._h, frame, None, 0, C.byref(n)))
+        out = np.zeros(n.value, CANDIDATE_DTYPE)
+        if n.value:
+            self._ck(self._lib.fd_tiled_download_candidates(self._h, frame, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
+    def keypoints(self, capacity: int):
+        kp = np.zeros((self.n_frames, capacity), KEYPOINT_DTYPE)
+        cnt = np.zeros(self.n_frames, np.int32)
+        self._ck(self._lib.fd_tiled_download_keypoints(self._h, kp.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.POINTER(C.c_int32)), capacity))
+        return kp, cnt
 
 
 class Context:

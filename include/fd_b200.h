@@ -158,6 +158,40 @@ fd_status fd_export_candidates(fd_context *ctx, uint64_t *dev_dst, int64_t dst_c
 fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, uint64_t *dev_keys, const uint32_t *dev_counts, uint32_t capacity,
                                int rows, int cols, int n_frames);
 
+/* ---- the same, as one call sequence over the GPUs of a box (fd_tiled.cu) ------------------------------
+ * Replaces, for frames too large (or too urgent) for one GPU, the dense stages of feature_point_harris_detector.cpp:17-137 /
+ * feature_point_shi_tomas_detector.cpp:17-137 / feature_point_fast_detector.cpp:83-98 and the global selection of
+ * feature_point_detector.cpp:54-74.  One process; tile k of every frame lives on device_ordinals[k] (ordinals may repeat: all tiles
+ * on one GPU is a valid, slower, configuration).  Rows are split into n_tiles contiguous blocks; each tile keeps its own rows plus a
+ * 3-row halo.  Own rows come from the host (fd_tiled_upload_frames: each device receives only its own rows) or from frames resident
+ * on one device (fd_tiled_scatter_device_frames: peer copies); the halo rows then travel tile to tile as device-to-device peer copies
+ * (NVLink when peer access is available), 2 x 3 x cols bytes per interior seam and frame, ordered by events.  fd_tiled_detect runs
+ * fd_compute_candidates per tile, packs the tiles' candidate keys on the first tile's device with a kernel that reads the other
+ * devices' key slots and counts through peer pointers (no count ever visits the host), and selects there.  Nothing synchronises with
+ * the host until a download / fd_tiled_sync.  Pre-existing features are not supported on tiles.  Results equal the untiled run
+ * (tests/test_tiled_abi.py). */
+typedef struct fd_tiled fd_tiled;
+fd_status fd_tiled_create(const int *device_ordinals, int n_tiles, fd_tiled **out);   /* n_tiles <= 16 */
+fd_status fd_tiled_destroy(fd_tiled *t);
+const char *fd_tiled_last_error(const fd_tiled *t);
+fd_status fd_tiled_upload_frames(fd_tiled *t, const uint8_t *host_frames, int rows, int cols, int n_frames);   /* synchronises (pageable source) */
+fd_status fd_tiled_scatter_device_frames(fd_tiled *t, const uint8_t *dev_frames, int rows, int cols, int64_t pitch, int64_t frame_stride, int n_frames);
+/* Where tile `tile` keeps its OWN rows (absolute rows [own_first_row, own_first_row + own_row_count) of every frame; row pitch and
+ * frame stride in bytes) and the stream its work is ordered on: a producer may rewrite the own rows in place on that stream and
+ * call fd_tiled_exchange_halos, which moves only the halo rows. */
+fd_status fd_tiled_tile_info(fd_tiled *t, int tile, int *device, int *own_first_row, int *own_row_count, uint8_t **dev_own_rows, int64_t *pitch,
+                             int64_t *frame_stride, void **cuda_stream);
+fd_status fd_tiled_exchange_halos(fd_tiled *t);
+uint64_t fd_tiled_halo_bytes(const fd_tiled *t);   /* bytes the last halo exchange moved between tiles */
+fd_status fd_tiled_compute_candidates(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile);   /* candidates + gather */
+fd_status fd_tiled_detect(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile);               /* ... + selection */
+fd_status fd_tiled_sync(fd_tiled *t);   /* FD_ERR_CAPACITY if a tile's candidate slot overflowed */
+fd_status fd_tiled_candidate_counts(fd_tiled *t, int32_t *host_counts);   /* per frame, all tiles together */
+fd_status fd_tiled_device_candidates(fd_tiled *t, const uint64_t **dev_keys, const uint32_t **dev_counts, uint32_t *capacity, int *device);
+fd_status fd_tiled_download_candidates(fd_tiled *t, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out);
+fd_status fd_tiled_download_keypoints(fd_tiled *t, fd_keypoint *host_kp, int32_t *host_counts, int kp_capacity);
+fd_context *fd_tiled_root_context(fd_tiled *t);   /* the first tile's context (holds the selected keypoints) */
+
 /* FeaturePointDetector::SparsifyFeatures (feature_point_detector.cpp:27-52): first-come grid filter over an
  * existing feature list.  Pure host-side integer logic over at most a few thousand points; kept in the
  * library so the drop-in class has one implementation.  status is in/out (n entries). */
