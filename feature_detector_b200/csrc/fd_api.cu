@@ -539,10 +539,9 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;
     a.xy_xor = xy_xor;
-    // Event-driven form for every frame whose cell grid fits shared memory; the forms of fd_select.cu take the rest (and all frames when
+    // Winner-driven form for every frame whose cell grid fits shared memory; the forms of fd_select.cu take the rest (and all frames when
     // FD_B200_SELECT_LEAN=0 asks for them: the parity tests hold the three forms against each other).
-    const bool lean = ctx->select_lean && p->min_feature_distance >= 0 && select_lean_smem_bytes(a.cells_x, a.cells_y) <= SELECT_LEAN_SMEM_MAX &&
-                      size_t(a.cells_x + 2) * (a.cells_y + 2) < 65536;
+    const bool lean = ctx->select_lean && p->min_feature_distance >= 0 && select_lean_grid_fits(a.cells_x, a.cells_y);
     a.lean_limit = lean ? 0xFFFFFFFFu : 0u;
     if (lean) {
         FD_CUDA(ctx, launch_select_lean(a, ctx->select_lean_threads, ctx->stream));
