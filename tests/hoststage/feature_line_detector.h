@@ -1,4 +1,4 @@
-// Drop-in for the reference's src/feature_line_detector/feature_line_detector.h:12-79: same class name, nested type names,
+// TEST SCAFFOLDING (not shipped): stand-in for the reference's src/feature_line_detector/feature_line_detector.h:12-79 -- same class name, nested type names,
 // Options and accessors, so a caller recompiles unchanged.  The dense stage (ComputeLineLevelAngleMap, .cpp:56-97) runs on
 // the GPU through LineLevelAngleField; region growing, rectangle fitting and validation (.cpp:99-228) are host code here as
 // they are in the reference -- the north star leaves them on the host -- written against the same PixelParam array the

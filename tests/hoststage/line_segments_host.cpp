@@ -1,4 +1,4 @@
-// Host stage of the drop-in FeatureLineDetector: seeds in, line segments out.  The dense stage that feeds it runs on the
+// TEST SCAFFOLDING (not shipped).  Host stage behind the line detector's dense stage: seeds in, line segments out.  The dense stage that feeds it runs on the
 // GPU (feature_line_field.cpp); everything here is pointer chasing over a few thousand pixels and stays on the host, as in
 // the reference (src/feature_line_detector/feature_line_detector.cpp:12-54, 99-228), whose arithmetic order is kept so that
 // the same seeds give the same segments.

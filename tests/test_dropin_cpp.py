@@ -51,8 +51,9 @@ def dropin_output_host_glue(built, image_png, tmp_path_factory):
     os.makedirs(build, exist_ok=True)
     exe = os.path.join(build, "fd_dropin_check_host_glue")
     srcs = [os.path.join(CPP, f) for f in ("fd_dropin_check.cpp", "feature_point_detector.cpp", "descriptor_brief.cpp", "feature_line_field.cpp",
-                                           "line_segments_host.cpp", "nn_feature_point_postprocess.cpp")]
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-Wall", "-I" + CPP, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "compat", "slam_utility"),
+                                           "nn_feature_point_postprocess.cpp")] + [os.path.join(ROOT, "tests", "hoststage", "line_segments_host.cpp")]
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-Wall", "-I" + CPP, "-I" + os.path.join(ROOT, "tests", "hoststage"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "compat", "slam_utility"),
            "-o", exe] + srcs + [os.path.join(ROOT, "tests", "hoststage", "fake_fd_abi.cpp"), "-L" + os.path.join(ROOT, "oracle"), "-lfd_oracle",
                                 "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -184,7 +185,7 @@ def _check_demos(out, kat, image_png, checker):
     assert abs(l["norm_sum"] - g["norm_sum"]) < 1e-3 and abs(l["angle_sum"] - g["angle_sum"]) < 1e-5 * g["n_valid"]
     assert l["descending"] is True and l["positions_ok"] is True
 
-    # the whole line detector (dense stage on the GPU, host stage in feature_detector_b200/cpp/line_segments_host.cpp):
+    # the whole line detector (dense stage on the GPU, host stage in tests/hoststage/line_segments_host.cpp, a stand-in for the reference's own):
     # 40 segments on image.png, and exactly the reference's where its build is available
     d = out["lsd_detect"]
     assert d["ok"] is True and d["n_lines"] == d["n_rectangles"] == 40 and d["n_seeds"] == 10087
@@ -194,3 +195,22 @@ def _check_demos(out, kat, image_png, checker):
         mine = np.array(d["lines"], np.float32).reshape(-1, 4)
         assert ok and mine.shape == ref_lines.shape
         assert np.array_equal(mine, ref_lines)      # same segments, same order, same bits
+
+
+@pytest.mark.gpu
+def test_route_b3_with_the_references_own_host_stage(image_png, tmp_path):
+    """INTEGRATION.md B.3 as a program (integration/route_b3.cpp, built into oracle/_ref/ where the reference is mounted): the
+    reference's FeatureLineDetector, compiled in place, with ComputeLineLevelAngleMap bound to LineLevelAngleField::Compute +
+    FillPixelParams.  On image.png (no equal-norm seed decides a segment there) it must return the reference's segments bit for bit."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "fd_route_b3")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fd_route_b3 was not built (needs /root/reference at build time)")
+    from feature_detector_b200.synth import synth
+    frames = np.stack([image_png, synth(752, 480, 3)])
+    raw = tmp_path / "frames.u8"
+    frames.tofile(raw)
+    r = subprocess.run([exe, str(raw), "480", "752", "2", "200"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["frames_with_identical_segments"] >= 1 and out["mean_lines"] > 10, out
+    assert out["route_b3_ms_per_frame"]["FillPixelParams"] > 0

@@ -1,4 +1,4 @@
-"""Host logic of the drop-in line detector on the CPU: feature_detector_b200/cpp/line_segments_host.cpp (region growing,
+"""Host logic behind the line detector's dense stage on the CPU: tests/hoststage/line_segments_host.cpp (test scaffolding: region growing,
 rectangle fit, validation -- the stage the north star leaves on the host) fed by the oracle's dense stage instead of kernel 5
 (tests/hoststage/hoststage_check.cpp replaces the one GPU-calling member function), against the reference's own segments:
 committed golden vectors (tests/golden/lsd_segments.npz, made by make_golden_lsd.py from oracle/_ref) and, where the reference
@@ -27,8 +27,9 @@ def hoststage(built):
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, "hoststage_check")
     cpp = os.path.join(ROOT, "feature_detector_b200", "cpp")
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-Wall", "-I" + cpp, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "compat", "slam_utility"),
-           "-o", exe, os.path.join(ROOT, "tests", "hoststage", "hoststage_check.cpp"), os.path.join(cpp, "line_segments_host.cpp"),
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-Wall", "-I" + cpp, "-I" + os.path.join(ROOT, "tests", "hoststage"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "compat", "slam_utility"),
+           "-o", exe, os.path.join(ROOT, "tests", "hoststage", "hoststage_check.cpp"), os.path.join(ROOT, "tests", "hoststage", "line_segments_host.cpp"),
            "-L" + os.path.join(ROOT, "oracle"), "-lfd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-4000:]
@@ -111,7 +112,7 @@ def test_host_glue_is_clean_under_asan_and_ubsan(built, image_png, tmp_path):
     two-column frame makes the reference itself write out of bounds in feature_line_detector.cpp:64-68; the drop-in guards that line)."""
     cpp = os.path.join(ROOT, "feature_detector_b200", "cpp")
     os.makedirs(BUILD, exist_ok=True)
-    flags = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I" + cpp, "-I" + os.path.join(ROOT, "include"),
+    flags = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I" + cpp, "-I" + os.path.join(ROOT, "tests", "hoststage"), "-I" + os.path.join(ROOT, "include"),
              "-I" + os.path.join(ROOT, "compat", "slam_utility")]
     link = ["-L" + os.path.join(ROOT, "oracle"), "-lfd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
     hs = os.path.join(BUILD, "hoststage_check_asan")
@@ -120,10 +121,11 @@ def test_host_glue_is_clean_under_asan_and_ubsan(built, image_png, tmp_path):
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if probe.returncode != 0:
         pytest.skip("this toolchain has no sanitizer runtime")
-    for exe, srcs in ((hs, [os.path.join(ROOT, "tests", "hoststage", "hoststage_check.cpp"), os.path.join(cpp, "line_segments_host.cpp")]),
+    hsdir = os.path.join(ROOT, "tests", "hoststage")
+    for exe, srcs in ((hs, [os.path.join(hsdir, "hoststage_check.cpp"), os.path.join(hsdir, "line_segments_host.cpp")]),
                       (full, [os.path.join(cpp, f) for f in ("fd_dropin_check.cpp", "feature_point_detector.cpp", "descriptor_brief.cpp", "feature_line_field.cpp",
-                                                             "line_segments_host.cpp", "nn_feature_point_postprocess.cpp")] +
-                             [os.path.join(ROOT, "tests", "hoststage", "fake_fd_abi.cpp")])):
+                                                             "nn_feature_point_postprocess.cpp")] +
+                             [os.path.join(hsdir, "line_segments_host.cpp"), os.path.join(hsdir, "fake_fd_abi.cpp")])):
         r = subprocess.run(flags + ["-o", exe] + srcs + link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode == 0, r.stdout[-3000:]
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
