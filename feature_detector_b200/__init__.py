@@ -70,6 +70,7 @@ class NnParams(C.Structure):
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("reserved", "<i4")])
 CANDIDATE_DTYPE = np.dtype([("response", "<f4"), ("x", "<i4"), ("y", "<i4")])
+MATCH_DTYPE = np.dtype([("train_index", "<i4"), ("distance", "<i4"), ("second_distance", "<i4"), ("reserved", "<i4")])
 
 
 def library_path() -> str:
@@ -126,6 +127,9 @@ def load_library():
                                                   C.POINTER(C.c_float)]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
+        "fd_match_consecutive": (C.c_int, [vp]),
+        "fd_match_descriptors": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
+        "fd_download_matches": (C.c_int, [vp, vp, C.c_int]),
         "fd_tiled_create": (C.c_int, [i32p, C.c_int, C.POINTER(vp)]),
         "fd_tiled_destroy": (C.c_int, [vp]),
         "fd_tiled_last_error": (C.c_char_p, [vp]),
@@ -444,6 +448,23 @@ class Context:
         self._ck(self._lib.fd_download_descriptors(self._h, desc.ctypes.data_as(C.c_void_p), desc.shape[1]))
 
     # -- NN detector post-processing ---------------------------------------------------------------------
+    # -- Hamming matching of the packed descriptors (no reference counterpart) ----------------------------
+    def match_selected(self):
+        """Frame f of the last described set against frame f + 1 (fd_match_consecutive); results stay on the device."""
+        self._ck(self._lib.fd_match_consecutive(self._h))
+
+    def matches(self, kp_capacity: int) -> np.ndarray:
+        """(n_frames - 1, kp_capacity) MATCH_DTYPE of the last match_selected()."""
+        out = np.zeros((max(self.n_frames - 1, 0), kp_capacity), MATCH_DTYPE)
+        buf = out if out.size else np.zeros((1, kp_capacity), MATCH_DTYPE)
+        self._ck(self._lib.fd_download_matches(self._h, buf.ctypes.data_as(C.c_void_p), kp_capacity))
+        return out
+
+    def match_descriptors(self, dev_desc_a: int, dev_counts_a: int, capacity_a: int, dev_desc_b: int, dev_counts_b: int, capacity_b: int, n_pairs: int,
+                          dev_out: int):
+        self._ck(self._lib.fd_match_descriptors(self._h, C.c_void_p(dev_desc_a), C.c_void_p(dev_counts_a), capacity_a, C.c_void_p(dev_desc_b),
+                                                C.c_void_p(dev_counts_b), capacity_b, n_pairs, C.c_void_p(dev_out)))
+
     def nn_select(self, dev_heatmap: int, rows: int, cols: int, n_frames: int, params: NnParams, cand_capacity: int = 0):
         """Heat maps (device pointer, n_frames x rows x cols float32) -> keypoints (fetch with keypoints())."""
         self._ck(self._lib.fd_nn_select_from_heatmap(self._h, C.c_void_p(dev_heatmap), rows, cols, n_frames, C.byref(params), cand_capacity))

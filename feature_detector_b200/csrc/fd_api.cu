@@ -84,7 +84,8 @@ struct fd_context {
     bool select_lean = true;        // FD_B200_SELECT_LEAN=0: testing knob, selection by the forms of fd_select.cu only
     int select_lean_threads = SELECT_LEAN_THREADS;   // FD_B200_SELECT_LEAN_THREADS: tuning knob
 
-    DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2];
+    DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2], matches;
+    int match_pairs = 0, match_capacity = 0;
     bool have_desc_float = false;
     int nn_channels = 0;
     bool have_nn_desc = false;
@@ -605,7 +606,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1]})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1], &ctx->matches})
         release(*b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -997,6 +998,66 @@ fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *
     if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
     if (dev_desc) *dev_desc = static_cast<const uint8_t *>(ctx->desc.ptr);
     if (kp_capacity) *kp_capacity = ctx->desc_capacity;
+    return FD_OK;
+}
+
+// ---- Hamming matching (no reference counterpart) ------------------------------------------------------
+fd_status fd_match_descriptors(fd_context *ctx, const uint8_t *dev_desc_a, const int32_t *dev_counts_a, int capacity_a, const uint8_t *dev_desc_b,
+                               const int32_t *dev_counts_b, int capacity_b, int n_pairs, fd_match *dev_out) {
+    if (!ctx || !dev_desc_a || !dev_counts_a || !dev_desc_b || !dev_counts_b || !dev_out || capacity_a <= 0 || capacity_b <= 0 || n_pairs < 0)
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_match_descriptors: bad argument");
+    if (size_t(capacity_b) * 32 > 200 * 1024) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_match_descriptors: a train set is limited to 6400 descriptors");
+    if ((reinterpret_cast<uintptr_t>(dev_desc_a) | reinterpret_cast<uintptr_t>(dev_desc_b) | reinterpret_cast<uintptr_t>(dev_out)) % 16 != 0)
+        return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_match_descriptors: descriptor sets and the output must be 16-byte aligned");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(fd_match) == sizeof(int4), "fd_match layout");
+    MatchArgs a = {};
+    a.desc_a = dev_desc_a;
+    a.desc_b = dev_desc_b;
+    a.counts_a = dev_counts_a;
+    a.counts_b = dev_counts_b;
+    a.capacity_a = capacity_a;
+    a.capacity_b = capacity_b;
+    a.n_pairs = n_pairs;
+    a.stride_a_sets = a.stride_b_sets = 1;
+    a.out = reinterpret_cast<int4 *>(dev_out);
+    FD_CUDA(ctx, launch_match(a, ctx->stream));
+    ++ctx->launches;
+    return FD_OK;
+}
+
+fd_status fd_match_consecutive(fd_context *ctx) {
+    if (!ctx) return FD_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_desc) return fail(ctx, FD_ERR_NOT_READY, "no descriptors computed");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int pairs = std::max(ctx->fv.n_frames - 1, 0), cap = ctx->desc_capacity;
+    if (size_t(cap) * 32 > 200 * 1024) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_match_consecutive: more than 6400 keypoint slots per frame");
+    FD_TRY(reserve(ctx, ctx->matches, size_t(std::max(pairs, 1)) * cap * sizeof(int4)));
+    MatchArgs a = {};
+    a.desc_a = a.desc_b = static_cast<const uint8_t *>(ctx->desc.ptr);
+    a.counts_a = a.counts_b = ctx->desc_counts;
+    a.capacity_a = a.capacity_b = cap;
+    a.n_pairs = pairs;
+    a.stride_a_sets = a.stride_b_sets = 1;
+    a.offset_b_sets = 1;
+    a.out = static_cast<int4 *>(ctx->matches.ptr);
+    FD_CUDA(ctx, launch_match(a, ctx->stream));
+    if (pairs > 0) ++ctx->launches;
+    ctx->match_pairs = pairs;
+    ctx->match_capacity = cap;
+    return FD_OK;
+}
+
+fd_status fd_download_matches(fd_context *ctx, fd_match *host_matches, int kp_capacity) {
+    if (!ctx || !host_matches || kp_capacity <= 0) return FD_ERR_INVALID_ARGUMENT;
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->match_capacity == 0) return fail(ctx, FD_ERR_NOT_READY, "fd_match_consecutive has not run");
+    if (ctx->match_pairs > 0) {
+        const int w = std::min(kp_capacity, ctx->match_capacity);
+        FD_CUDA(ctx, cudaMemcpy2DAsync(host_matches, size_t(kp_capacity) * sizeof(fd_match), ctx->matches.ptr, size_t(ctx->match_capacity) * sizeof(fd_match),
+                                       size_t(w) * sizeof(fd_match), size_t(ctx->match_pairs), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FD_OK;
 }
 

@@ -158,6 +158,17 @@ cudaError_t launch_brief(const BriefArgs &args, cudaStream_t stream);
 // The std::vector<Vec> overload of Descriptor::Compute (descriptor.h:43-62): packed bits -> +1 / -1 floats, `length` per keypoint slot.
 cudaError_t launch_brief_to_float(const uint8_t *desc, const int32_t *kp_counts, int kp_capacity, int n_frames, int length, float *out, cudaStream_t stream);
 
+// ---- Hamming matching of packed descriptors (no reference counterpart), fd_match.cu -------------------------
+struct MatchArgs {
+    const uint8_t *desc_a, *desc_b;       // descriptor sets: slots of capacity x 32 bytes
+    const int32_t *counts_a, *counts_b;   // valid descriptors per set
+    int capacity_a, capacity_b;
+    int n_pairs;                          // pair i matches set i * stride_a_sets of A against set i * stride_b_sets + offset_b_sets of B
+    int stride_a_sets, stride_b_sets, offset_b_sets;
+    int4 *out;                            // n_pairs x capacity_a: (train index or -1, distance, second distance or -1, 0)
+};
+cudaError_t launch_match(const MatchArgs &args, cudaStream_t stream);
+
 // ---- kernel 5: LSD gradient / level-line field --------------------------------------------------
 constexpr int LSD_THREADS = 256;
 constexpr int LSD_MAX_M = 2 * 255 * 255;   // largest ad^2 + bc^2 (feature_line_detector.cpp:76-82 on 8-bit pixels)

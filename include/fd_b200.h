@@ -242,6 +242,26 @@ fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *h
  * holds n_frames x channels planes of map_rows x map_cols floats (the model's 1/8-resolution descriptor volume); the
  * output is `channels` floats per keypoint slot, in dev_out (n_frames * kp_capacity * channels floats) or, if NULL, in a
  * context-owned buffer that fd_nn_download_descriptors copies out. */
+/* ---- Hamming matching of the packed descriptors ------------------------------------------------------
+ * The step after Descriptor<BriefType>::Compute for any caller.  The reference has NO matcher (descriptor.h:43-62, the +1 / -1
+ * float form, is its only consumer-facing transform), so this entry point has no reference parity; its checker is a numpy
+ * XOR / popcount restatement.  For every query descriptor: the nearest train descriptor by Hamming distance over the 256 bits (lowest
+ * index among equal distances), that distance and the second-smallest distance; index -1 where there is no query or no train set. */
+typedef struct fd_match {
+    int32_t train_index;      /* -1: no match */
+    int32_t distance;         /* 0 .. 256, -1 without a match */
+    int32_t second_distance;  /* -1 when the train set has fewer than two descriptors */
+    int32_t reserved;
+} fd_match;
+/* Frame f of the last described set (fd_describe_selected / fd_describe_points) against frame f + 1: n_frames - 1 pairs, results in a
+ * context-owned device buffer of (n_frames - 1) x kp_capacity fd_match (fd_download_matches copies it out; synchronises). */
+fd_status fd_match_consecutive(fd_context *ctx);
+/* Caller-supplied device sets: n_pairs query sets of capacity_a x 32 bytes against n_pairs train sets of capacity_b x 32 bytes;
+ * dev_out receives n_pairs x capacity_a fd_match. */
+fd_status fd_match_descriptors(fd_context *ctx, const uint8_t *dev_desc_a, const int32_t *dev_counts_a, int capacity_a, const uint8_t *dev_desc_b,
+                               const int32_t *dev_counts_b, int capacity_b, int n_pairs, fd_match *dev_out);
+fd_status fd_download_matches(fd_context *ctx, fd_match *host_matches, int kp_capacity);
+
 typedef struct fd_nn_params {
     float min_response;           /* Options::kMinResponse, default 0.1f (nn_feature_point_detector.h:28) */
     int32_t invalid_boundary;     /* kInvalidBoundary, default 3 */

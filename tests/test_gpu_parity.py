@@ -770,3 +770,66 @@ def test_results_do_not_depend_on_scheduling(monkeypatch):
                 if base is None:
                     base = snap
                 assert same(base, snap), (items, rep)
+
+
+# ---- Hamming matching of the packed descriptors (fd_match.cu; SURVEY.md 8f-4 -- the reference has no matcher, numpy is the checker) ----
+def _numpy_matches(desc, counts, capacity):
+    """For every descriptor of frame f the nearest one of frame f + 1 by Hamming distance (lowest index on ties), that distance and the
+    second-smallest distance -- XOR + popcount over the 32 bytes."""
+    lut = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    out = np.zeros((len(desc) - 1, capacity), fd.MATCH_DTYPE)
+    out["train_index"], out["distance"], out["second_distance"] = -1, -1, -1
+    for f in range(len(desc) - 1):
+        a, b = desc[f, :counts[f]], desc[f + 1, :counts[f + 1]]
+        if len(a) == 0 or len(b) == 0:
+            continue
+        dist = lut[a[:, None, :] ^ b[None, :, :]].sum(-1)
+        idx = dist.argmin(1)
+        out["train_index"][f, :len(a)] = idx
+        out["distance"][f, :len(a)] = dist[np.arange(len(a)), idx]
+        if len(b) > 1:
+            out["second_distance"][f, :len(a)] = np.sort(dist, 1)[:, 1]
+    return out
+
+
+def test_hamming_matches_vs_numpy(ctx, torch_cuda):
+    from feature_detector_b200.synth import synth
+    torch = torch_cuda
+    frames = np.stack([synth(752, 480, 300 + i // 2) for i in range(7)])        # pairs of equal frames among them: distance 0 matches
+    frames[3] = 0                                                                # a frame without keypoints: no matches into or out of it
+    ctx.upload(frames)
+    ctx.set_existing_features([])
+    ctx.detect(fd.DetectParams(fd.FAST, 10.0, 20, 150, fast_n=9))
+    ctx.describe_selected(fd.BriefParams(256, 8))
+    kp, cnt = ctx.keypoints(150)
+    desc = ctx.descriptors(150)
+    ctx.match_selected()
+    got = ctx.matches(150)
+    want = _numpy_matches(desc, cnt, 150)
+    for name in ("train_index", "distance", "second_distance"):
+        assert np.array_equal(got[name], want[name]), name
+    same = got["distance"][0, :cnt[0]]
+    assert cnt[0] > 50 and np.all(same == 0) and np.array_equal(got["train_index"][0, :cnt[0]], np.arange(cnt[0]))   # frame 0 == frame 1
+    assert np.all(got["train_index"][2] == -1) and np.all(got["train_index"][3] == -1)
+    # caller-supplied sets: random descriptors, different capacities
+    rng = np.random.default_rng(3)
+    a = torch.from_numpy(rng.integers(0, 256, (5, 40, 32), dtype=np.uint8)).cuda()
+    b = torch.from_numpy(rng.integers(0, 256, (5, 333, 32), dtype=np.uint8)).cuda()
+    ca = torch.tensor([40, 0, 7, 40, 1], dtype=torch.int32).cuda()
+    cb = torch.tensor([333, 10, 0, 1, 200], dtype=torch.int32).cuda()
+    out = torch.zeros((5, 40, 4), dtype=torch.int32).cuda()
+    torch.cuda.synchronize()
+    ctx.match_descriptors(a.data_ptr(), ca.data_ptr(), 40, b.data_ptr(), cb.data_ptr(), 333, 5, out.data_ptr())
+    ctx.sync()
+    o = out.cpu().numpy()
+    lut = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    an, bn = a.cpu().numpy(), b.cpu().numpy()
+    for p_ in range(5):
+        na, nb = int(ca[p_]), int(cb[p_])
+        for q in range(40):
+            if q >= na or nb == 0:
+                assert o[p_, q, 0] == -1 and o[p_, q, 1] == -1
+                continue
+            dist = lut[an[p_, q][None, :] ^ bn[p_, :nb]].sum(-1)
+            assert o[p_, q, 0] == dist.argmin() and o[p_, q, 1] == dist.min()
+            assert o[p_, q, 2] == (np.sort(dist)[1] if nb > 1 else -1)
