@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "basic_type.h"
@@ -67,16 +68,43 @@ public:
             pixels(pr - 1, i).col = i;
             pixels(pr - 1, i).row = pr - 1;
         }
-        for (int32_t col = 1; col < cols_ - 2; ++col) {                           // .cpp:71-89, same column-major walk
-            for (int32_t row = 1; row < rows_ - 2; ++row) {
-                auto &px = pixels(row, col);
-                const size_t at = size_t(row) * size_t(cols_) + size_t(col);
-                px.row = row;
-                px.col = col;
-                px.gradient_norm = norm_[at];
-                px.is_valid = norm_[at] > options_.kMinValidGradientNorm;
-                if (px.is_valid) px.line_level_angle = angle_[at];
+        // .cpp:71-89.  The reference walks columns outer / rows inner over a row-major image and a column-major matrix; every
+        // pixel's record is written independently of the others, so the same records are produced here tile by tile (the rows of a
+        // tile stay in cache while its columns are walked) and, for large frames, by a few threads that split the columns.
+        const int32_t c_lo = 1, c_hi = cols_ - 2, r_lo = 1, r_hi = rows_ - 2;
+        const float min_norm = options_.kMinValidGradientNorm;
+        auto fill_columns = [&](int32_t col_begin, int32_t col_end) {
+            constexpr int32_t kTileCols = 16, kTileRows = 256;
+            for (int32_t col0 = col_begin; col0 < col_end; col0 += kTileCols) {
+                const int32_t col1 = std::min(col0 + kTileCols, col_end);
+                for (int32_t row0 = r_lo; row0 < r_hi; row0 += kTileRows) {
+                    const int32_t row1 = std::min(row0 + kTileRows, r_hi);
+                    for (int32_t col = col0; col < col1; ++col) {
+                        for (int32_t row = row0; row < row1; ++row) {
+                            auto &px = pixels(row, col);
+                            const size_t at = size_t(row) * size_t(cols_) + size_t(col);
+                            px.row = row;
+                            px.col = col;
+                            px.gradient_norm = norm_[at];
+                            px.is_valid = norm_[at] > min_norm;
+                            if (px.is_valid) px.line_level_angle = angle_[at];
+                        }
+                    }
+                }
             }
+        };
+        const int64_t interior = int64_t(std::max(c_hi - c_lo, 0)) * std::max(r_hi - r_lo, 0);
+        const unsigned n_threads = interior < (int64_t(1) << 18) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n_threads <= 1 || c_hi <= c_lo) {
+            if (c_hi > c_lo) fill_columns(c_lo, c_hi);
+        } else {
+            std::vector<std::thread> workers;
+            const int32_t per = (c_hi - c_lo + int32_t(n_threads) - 1) / int32_t(n_threads);
+            for (unsigned t = 0; t < n_threads; ++t) {
+                const int32_t b = c_lo + int32_t(t) * per, e = std::min(b + per, c_hi);
+                if (b < e) workers.emplace_back(fill_columns, b, e);
+            }
+            for (std::thread &w : workers) w.join();
         }
         const size_t before = sorted.size();
         for (const int32_t s : seeds_) sorted.emplace_back(&pixels(s / cols_, s % cols_));   // .cpp:86, already in :92-94 order

@@ -81,8 +81,6 @@ struct fd_context {
     int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
-    bool select_lean = true;        // FD_B200_SELECT_LEAN=0: testing knob, selection by the forms of fd_select.cu only
-    int select_lean_threads = SELECT_LEAN_THREADS;   // FD_B200_SELECT_LEAN_THREADS: tuning knob
 
     DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2], matches;
     int match_pairs = 0, match_capacity = 0;
@@ -540,17 +538,8 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;
     a.xy_xor = xy_xor;
-    // Winner-driven form for every frame whose cell grid fits shared memory; the forms of fd_select.cu take the rest (and all frames when
-    // FD_B200_SELECT_LEAN=0 asks for them: the parity tests hold the three forms against each other).
-    const bool lean = ctx->select_lean && p->min_feature_distance >= 0 && select_lean_grid_fits(a.cells_x, a.cells_y);
-    a.lean_limit = lean ? 0xFFFFFFFFu : 0u;
-    if (lean) {
-        FD_CUDA(ctx, launch_select_lean(a, ctx->select_lean_threads, ctx->stream));
-        ++ctx->launches;
-    } else {
-        FD_CUDA(ctx, launch_select(a, ctx->stream));
-        ctx->launches += (a.cand_capacity > a.cells_min) ? 2 : 1;   // the per-cell form is launched only when the capacity admits it
-    }
+    FD_CUDA(ctx, launch_select(a, ctx->stream));
+    ctx->launches += (a.cand_capacity > a.cells_min) ? 2 : 1;   // the per-cell form is launched only when the capacity admits it
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
     ctx->select_frames = fv.n_frames;
@@ -592,8 +581,6 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
-    if (const char *env = std::getenv("FD_B200_SELECT_LEAN")) ctx->select_lean = (env[0] != '0');
-    if (const char *env = std::getenv("FD_B200_SELECT_LEAN_THREADS")) ctx->select_lean_threads = std::min(SELECT_LEAN_MAX_THREADS, std::max(64, atoi(env) / 32 * 32));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     *out_ctx = ctx;

@@ -130,19 +130,10 @@ struct SelectArgs {
     int cells_in_smem;
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
-    uint32_t lean_limit;            // frames with fewer candidates than this go to the event-driven kernel (fd_select_lean.cu); 0 = none
     uint32_t xy_xor;                // 0, or 0xFFFFFFFF when the keys carry the complemented position (NN heat maps: among equal responses the later pixel first)
 };
 size_t select_cell_bytes(int cells_x, int cells_y);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
-// Event-driven form (fd_select_lean.cu): frames with fewer than lean_limit candidates whose cell grid fits shared memory.
-constexpr int SELECT_LEAN_MAX_THREADS = 256;
-constexpr int SELECT_LEAN_MIN_CTAS = 6;   // resident CTAs per SM the register budget is set for (a frame per CTA: more frames in flight hide the rounds' latency)
-constexpr int SELECT_LEAN_THREADS = 256;
-constexpr size_t SELECT_LEAN_SMEM_MAX = 96 * 1024;
-size_t select_lean_smem_bytes(int cells_x, int cells_y);
-bool select_lean_grid_fits(int cells_x, int cells_y);
-cudaError_t launch_select_lean(const SelectArgs &args, int threads, cudaStream_t stream);
 
 // ---- kernel 4: steered BRIEF --------------------------------------------------------------------
 struct BriefArgs {

@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     const uint32_t count = p.cand_counts[frame];
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
-    if (n < p.lean_limit) return;   // fd_select_lean.cu takes the frame
     if ((n > p.cells_min) != BY_CELLS) return;
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
     // binned: the admitted candidates grouped by cell; admitted: the same keys in arrival order, before grouping

@@ -1,5 +1,4 @@
-// Device helpers shared by the two selection kernels (fd_select.cu: rounds over all live candidates / all cells;
-// fd_select_lean.cu: event-driven rounds over the cells a fresh point touches).
+// Device helpers of the selection kernel (fd_select.cu).
 #pragma once
 
 #include "fd_kernels.cuh"

@@ -14,6 +14,7 @@
 // (total / GPU field incl. upload and download / FillPixelParams / the reference's host stage), and whether the segments agree.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,7 @@
 
 namespace {
 bool g_route_b3 = true;
+bool g_canonical_ties = false;   // reference mode: re-order equal-norm seeds the way this framework orders them (push order)
 double g_ref_map_s = 0.0, g_field_s = 0.0, g_fill_s = 0.0;
 double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
@@ -39,6 +41,11 @@ bool FeatureLineDetector::ComputeLineLevelAngleMap(const GrayImage &image) {
         const double t0 = Now();
         const bool ok = reference(this, image);
         g_ref_map_s += Now() - t0;
+        if (g_canonical_ties)   // the reference's std::sort (.cpp:92-94) is unstable: fix the order inside runs of equal norm
+            std::sort(sorted_pixels_.begin(), sorted_pixels_.end(), [](const PixelParam *a, const PixelParam *b) {
+                if (a->gradient_norm != b->gradient_norm) return a->gradient_norm > b->gradient_norm;
+                return a->col != b->col ? a->col < b->col : a->row < b->row;
+            });
         return ok;
     }
     // ---- the body INTEGRATION.md B.3 gives ----
@@ -82,16 +89,25 @@ int main(int argc, char **argv) {
         g_field_s = g_fill_s = 0.0;
     }
     double ref_total = 0.0, b3_total = 0.0;
-    size_t n_lines = 0, n_equal = 0;
+    size_t n_lines = 0, n_equal = 0, n_equal_tied = 0;
     for (int i = 0; i < n; ++i) {
         GrayImage image(frames.data() + size_t(i) * rows * cols, rows, cols, false);
-        std::vector<Vec4> ref_lines, b3_lines;
+        std::vector<Vec4> ref_lines, tied_lines, b3_lines;
         {   // a fresh detector per frame, as the demo creates it: the reference never clears sorted_pixels_
             g_route_b3 = false;
             FeatureLineDetector detector;
             const double t0 = Now();
             if (!detector.DetectGoodFeatures(image, needed, ref_lines)) return 1;
             ref_total += Now() - t0;
+        }
+        {   // the reference again, with equal-norm seeds in this framework's order: what route B.3 has to reproduce bit for bit
+            g_route_b3 = false;
+            g_canonical_ties = true;
+            const double keep = g_ref_map_s;
+            FeatureLineDetector detector;
+            if (!detector.DetectGoodFeatures(image, needed, tied_lines)) return 1;
+            g_ref_map_s = keep;
+            g_canonical_ties = false;
         }
         {
             g_route_b3 = true;
@@ -104,15 +120,18 @@ int main(int argc, char **argv) {
         bool same = ref_lines.size() == b3_lines.size();
         for (size_t k = 0; same && k < ref_lines.size(); ++k) same = std::memcmp(ref_lines[k].data(), b3_lines[k].data(), 4 * sizeof(float)) == 0;
         n_equal += same ? 1 : 0;
+        bool same_tied = tied_lines.size() == b3_lines.size();
+        for (size_t k = 0; same_tied && k < tied_lines.size(); ++k) same_tied = std::memcmp(tied_lines[k].data(), b3_lines[k].data(), 4 * sizeof(float)) == 0;
+        n_equal_tied += same_tied ? 1 : 0;
     }
     const double ms = 1e3 / n;
     std::printf("{\"frames\": %d, \"rows\": %d, \"cols\": %d, \"needed\": %u, \"mean_lines\": %.1f, "
                 "\"reference_ms_per_frame\": {\"DetectGoodFeatures\": %.3f, \"ComputeLineLevelAngleMap\": %.3f, \"host_stage\": %.3f}, "
                 "\"route_b3_ms_per_frame\": {\"DetectGoodFeatures\": %.3f, \"gpu_field_upload_kernels_download\": %.3f, \"FillPixelParams\": %.3f, \"host_stage\": %.3f}, "
-                "\"frames_with_identical_segments\": %zu, \"segments_equal_reference\": %s, "
+                "\"frames_with_identical_segments\": %zu, \"frames_identical_given_the_same_tie_order\": %zu, \"segments_equal_reference\": %s, "
                 "\"note\": \"host_stage = the reference's own region growing / rectangle fit, compiled in place; equal-norm seeds may be ordered differently by the "
-                "reference's unstable std::sort (feature_line_detector.cpp:92-94), which can change segments on frames with such ties\"}\n",
+                "reference's unstable std::sort (feature_line_detector.cpp:92-94), which can change segments on frames with such ties: frames_identical_given_the_same_tie_order compares with the reference run on the seed order this framework fixes (ties in push order); a last-ulp difference of the kernel's arctangent (<= 5e-7 rad, budget 1e-5) can still move a pixel across the 22.5 degree tolerance\"}\n",
                 n, rows, cols, needed, double(n_lines) / n, ref_total * ms, g_ref_map_s * ms, (ref_total - g_ref_map_s) * ms, b3_total * ms, g_field_s * ms, g_fill_s * ms,
-                (b3_total - g_field_s - g_fill_s) * ms, n_equal, n_equal == size_t(n) ? "true" : "false");
+                (b3_total - g_field_s - g_fill_s) * ms, n_equal, n_equal_tied, n_equal_tied == size_t(n) ? "true" : "false");
     return 0;
 }

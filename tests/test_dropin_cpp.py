@@ -212,5 +212,5 @@ def test_route_b3_with_the_references_own_host_stage(image_png, tmp_path):
     r = subprocess.run([exe, str(raw), "480", "752", "2", "200"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["frames_with_identical_segments"] >= 1 and out["mean_lines"] > 10, out
+    assert out["frames_identical_given_the_same_tie_order"] >= 1 and out["mean_lines"] > 10, out
     assert out["route_b3_ms_per_frame"]["FillPixelParams"] > 0

@@ -557,17 +557,14 @@ def test_corner_kernels_agree_with_and_without_masks(ctx):
         stream_ctx.close()
 
 
-# ---- the three forms of the selection rounds: event-driven (fd_select_lean.cu, the default), per live candidate and per cell (fd_select.cu) ----
+# ---- the two forms of the selection rounds (fd_select.cu): per live candidate and per cell -------------------------------
 def _ctx_with_select_threshold(value):
-    """A context that selects with the forms of fd_select.cu only: per cell above `value` candidates, per candidate below."""
     import os
     os.environ["FD_B200_SELECT_CELLS_MIN"] = str(value)
-    os.environ["FD_B200_SELECT_LEAN"] = "0"
     try:
         return fd.Context(0)
     finally:
         del os.environ["FD_B200_SELECT_CELLS_MIN"]
-        del os.environ["FD_B200_SELECT_LEAN"]
 
 
 def test_selection_per_cell_equals_per_candidate(checker):
@@ -575,7 +572,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
     same candidates must give the same keypoints, with and without pre-existing features, for one and for several rank
     batches, fine and coarse cell grids."""
     from feature_detector_b200.synth import synth
-    per_cell, per_cand, lean = _ctx_with_select_threshold(0), _ctx_with_select_threshold(1 << 30), fd.Context(0)
+    per_cell, per_cand, default = _ctx_with_select_threshold(0), _ctx_with_select_threshold(1 << 30), fd.Context(0)
     try:
         rng = np.random.default_rng(11)
         batches = [np.stack([synth(320, 200, i) for i in range(6)]),
@@ -589,7 +586,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
             for kind, thr, d, n, fast_n in cases:
                 for with_existing in (False, True):
                     out = []
-                    for c in (per_cell, per_cand, lean):
+                    for c in (per_cell, per_cand, default):
                         c.upload(frames)
                         if with_existing:
                             c.set_existing_features(existing)
@@ -614,7 +611,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
                 assert np.array_equal(feats, o["features"]), f
             # min distance 0 and 1: cells of one and two pixels (the cell index is the pixel itself at 0), both forms against the checker
             for d in (0, 1):
-                for c in (per_cell, per_cand, lean):
+                for c in (per_cell, per_cand, default):
                     c.upload(frames)
                     c.set_existing_features([])
                     c.detect(fd.DetectParams(fd.FAST, 5.0, d, 400, fast_n=9), 0)
@@ -626,7 +623,7 @@ def test_selection_per_cell_equals_per_candidate(checker):
     finally:
         per_cell.close()
         per_cand.close()
-        lean.close()
+        default.close()
 
 
 def test_host_pipeline_equals_single_call(ctx, torch_cuda):

@@ -164,7 +164,7 @@ def main():
             part()
             checked += ctx.check_guards()
     # the alternative instantiations behind the testing knobs
-    os.environ.update(FD_B200_FAST_DENSE="1", FD_B200_CORNER_STREAM="1", FD_B200_SELECT_CELLS_MIN="0", FD_B200_SELECT_LEAN="0")
+    os.environ.update(FD_B200_FAST_DENSE="1", FD_B200_CORNER_STREAM="1", FD_B200_SELECT_CELLS_MIN="0")
     with fd.Context(0) as ctx:
         detectors(ctx, "dense FAST, streaming corner, per-cell selection")
         checked += ctx.check_guards()
