@@ -323,7 +323,11 @@ void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_fr
     const int64_t total_warps = int64_t(grid) * warps_per_cta;
     const int64_t base_items = int64_t(n_frames) * n_strips;
     int64_t want_bands = (ctx->items_per_warp * total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
-    want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, std::max(1, interior_rows / min_band)));
+    int64_t max_bands = std::max(1, interior_rows / min_band);
+    // A few frames (the drop-in classes' one frame per call) cannot fill the grid with bands that tall: what counts there is the
+    // latency of the longest band, not the halo rows shorter bands read twice.
+    if (base_items * max_bands < total_warps) max_bands = std::max(1, interior_rows / std::max(8, min_band / 4));
+    want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, max_bands));
     band_rows = int((interior_rows + want_bands - 1) / want_bands);
     band_rows = std::max(band_rows, 1);
     band_rows = (band_rows + band_multiple - 1) / band_multiple * band_multiple;  // kernels that unroll their row loop
