@@ -272,6 +272,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     cpu_group = None
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # NCCL's default prints its version on stdout, next to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")     # host-side barriers while one rank drives all GPUs (tiled path)
