@@ -127,6 +127,7 @@ def load_library():
                                                   C.POINTER(C.c_float)]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
+        "fd_detect_describe_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.POINTER(BriefParams), C.c_int, vp, i32p, vp, C.c_int]),
         "fd_match_consecutive": (C.c_int, [vp]),
         "fd_match_descriptors": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
         "fd_download_matches": (C.c_int, [vp, vp, C.c_int]),
@@ -448,6 +449,21 @@ class Context:
         self._ck(self._lib.fd_download_descriptors(self._h, desc.ctypes.data_as(C.c_void_p), desc.shape[1]))
 
     # -- NN detector post-processing ---------------------------------------------------------------------
+    def detect_describe_host(self, frames, detect: DetectParams, brief: BriefParams | None, kp_capacity: int, cand_capacity: int = 0):
+        """One host-to-host call (fd_detect_describe_host): returns (keypoints (n, cap) KEYPOINT_DTYPE, counts (n,), descriptors (n, cap, 32) or None)."""
+        a = np.ascontiguousarray(frames, np.uint8)
+        if a.ndim == 2:
+            a = a[None]
+        n, rows, cols = a.shape
+        kp = np.zeros((n, kp_capacity), KEYPOINT_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        desc = np.zeros((n, kp_capacity, 32), np.uint8) if brief is not None else None
+        self._ck(self._lib.fd_detect_describe_host(self._h, a.ctypes.data_as(C.c_void_p), rows, cols, n, C.byref(detect), C.byref(brief) if brief is not None else None,
+                                                   cand_capacity, kp.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                   desc.ctypes.data_as(C.c_void_p) if desc is not None else None, kp_capacity))
+        self.rows, self.cols, self.n_frames = rows, cols, n
+        return kp, cnt, desc
+
     # -- Hamming matching of the packed descriptors (no reference counterpart) ----------------------------
     def match_selected(self):
         """Frame f of the last described set against frame f + 1 (fd_match_consecutive); results stay on the device."""

@@ -82,6 +82,8 @@ struct fd_context {
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
 
+    void *host_stage = nullptr;     // pinned staging block of fd_detect_describe_host
+    size_t host_stage_bytes = 0;
     DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2], matches;
     int match_pairs = 0, match_capacity = 0;
     bool have_desc_float = false;
@@ -599,6 +601,7 @@ fd_status fd_destroy(fd_context *ctx) {
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
                       &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1], &ctx->matches})
         release(*b);
+    if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FD_OK;
@@ -827,8 +830,9 @@ fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *
     if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;
     FD_CUDA(ctx, cudaSetDevice(ctx->device));   // a process may hold contexts on several devices
     if (!ctx->have_keypoints) return fail(ctx, FD_ERR_NOT_READY, "fd_detect has not run");
-    FD_TRY(check_overflow(ctx));
     const int nf = ctx->select_frames;
+    uint32_t overflow = 0;   // read in the same round trip as the results (one synchronisation per call: it is most of a one-frame call's cost)
+    if (ctx->flags.ptr != nullptr) FD_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(ctx, cudaMemcpyAsync(host_counts, ctx->kp_counts.ptr, size_t(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_kp != nullptr) {
         static_assert(sizeof(fd_keypoint) == sizeof(float4), "fd_keypoint layout");
@@ -841,6 +845,7 @@ fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *
         }
     }
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (overflow != 0) return fail(ctx, FD_ERR_CAPACITY, "a frame produced more candidates than cand_capacity; raise it and run again");
     if (host_kp != nullptr)
         for (int f = 0; f < nf; ++f)
             if (host_counts[f] > kp_capacity) return fail(ctx, FD_ERR_CAPACITY, "host keypoint buffer too small");
@@ -917,6 +922,52 @@ fd_status fd_describe_selected(fd_context *ctx, const fd_brief_params *params) {
         return fail(ctx, FD_ERR_NOT_READY, "the selected keypoints do not belong to the bound frames: bind the full frames and use fd_describe_points");
     ctx->desc_from_user = false;
     return run_brief(ctx, params, static_cast<const float4 *>(ctx->kp.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), ctx->kp_capacity);
+}
+
+fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames, const fd_detect_params *det,
+                                  const fd_brief_params *brief, int cand_capacity, fd_keypoint *host_kp, int32_t *host_counts, uint8_t *host_desc,
+                                  int kp_capacity) {
+    if (!ctx || !host_kp || !host_counts || kp_capacity <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_detect_describe_host: bad argument");
+    if ((brief == nullptr) != (host_desc == nullptr)) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_detect_describe_host: brief parameters and host_desc go together");
+    FD_TRY(fd_upload_frames(ctx, host_frames, rows, cols, n_frames));
+    if (ctx->tiled) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_detect_describe_host on a row tile");
+    FD_TRY(run_candidates(ctx, det, cand_capacity));
+    FD_TRY(run_select(ctx, det, rows, cols, n_frames, static_cast<uint64_t *>(ctx->keys.ptr), static_cast<const uint32_t *>(ctx->counts.ptr), ctx->cand_capacity));
+    ctx->kp_of_bound_frames = true;
+    if (brief != nullptr) {
+        ctx->desc_from_user = false;
+        FD_TRY(run_brief(ctx, brief, static_cast<const float4 *>(ctx->kp.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), ctx->kp_capacity));
+    }
+    // every result comes back through one pinned staging block and ONE synchronisation
+    const int w = std::min(kp_capacity, ctx->kp_capacity);
+    const size_t kp_bytes = size_t(n_frames) * w * sizeof(float4), cnt_bytes = size_t(n_frames) * 4, desc_bytes = brief ? size_t(n_frames) * w * 32 : 0;
+    const size_t need = 16 + kp_bytes + cnt_bytes + desc_bytes;
+    if (need > ctx->host_stage_bytes) {
+        if (ctx->host_stage) FD_CUDA(ctx, cudaFreeHost(ctx->host_stage));
+        ctx->host_stage = nullptr;
+        ctx->host_stage_bytes = 0;
+        FD_CUDA(ctx, cudaMallocHost(&ctx->host_stage, need));
+        ctx->host_stage_bytes = need;
+    }
+    uint8_t *st = static_cast<uint8_t *>(ctx->host_stage);
+    FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaMemcpyAsync(st + 16, ctx->kp_counts.ptr, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes, size_t(w) * sizeof(float4), ctx->kp.ptr, size_t(ctx->kp_capacity) * sizeof(float4), size_t(w) * sizeof(float4),
+                                   size_t(n_frames), cudaMemcpyDeviceToHost, ctx->stream));
+    if (brief != nullptr)
+        FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes + kp_bytes, size_t(w) * 32, ctx->desc.ptr, size_t(ctx->desc_capacity) * 32, size_t(w) * 32, size_t(n_frames),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t overflow;
+    std::memcpy(&overflow, st, 4);
+    if (overflow != 0) return fail(ctx, FD_ERR_CAPACITY, "a frame produced more candidates than cand_capacity; raise it and run again");
+    std::memcpy(host_counts, st + 16, cnt_bytes);
+    for (int f = 0; f < n_frames; ++f) {
+        if (host_counts[f] > kp_capacity) return fail(ctx, FD_ERR_CAPACITY, "host keypoint buffer too small");
+        std::memcpy(host_kp + size_t(f) * kp_capacity, st + 16 + cnt_bytes + size_t(f) * w * sizeof(float4), size_t(w) * sizeof(float4));
+        if (brief != nullptr) std::memcpy(host_desc + size_t(f) * kp_capacity * 32, st + 16 + cnt_bytes + kp_bytes + size_t(f) * w * 32, size_t(w) * 32);
+    }
+    return FD_OK;
 }
 
 fd_status fd_describe_points(fd_context *ctx, const fd_brief_params *params, const float *host_xy, const int32_t *host_counts, int capacity,

@@ -460,7 +460,9 @@ size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_
 
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(args);
-    const int threads = args.cells_in_smem ? SELECT_THREADS : SELECT_MAX_THREADS;
+    // one CTA per frame: with fewer frames than SMs (the drop-in classes' one frame per call) a CTA has its SM to itself, and the
+    // passes that stream over a frame's candidates are what its latency is made of
+    const int threads = (args.cells_in_smem && args.n_frames > 148) ? SELECT_THREADS : SELECT_MAX_THREADS;
     cudaError_t e = cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     select_kernel<false><<<args.n_frames, threads, smem, stream>>>(args);

@@ -139,6 +139,15 @@ fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_
 fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts);
 fd_status fd_device_keypoints(fd_context *ctx, const fd_keypoint **dev_kp, const int32_t **dev_counts, int *kp_capacity);
 
+/* The reference's call pattern -- one frame (or a few) per call, DetectGoodFeatures (feature_point_detector.cpp:7-25) followed by
+ * Descriptor::Compute (descriptor.h:28-40) on the same image -- as ONE host-to-host call: upload, candidates, selection, BRIEF and the
+ * downloads of counts, keypoints and descriptors with a single synchronisation (the separate calls synchronise three times, which is a
+ * fifth of a one-frame call).  brief and host_desc are both null to skip the descriptors.  host_kp / host_desc are n_frames slots of
+ * kp_capacity entries; pre-existing features (fd_set_existing_features) apply as in fd_detect. */
+fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames, const fd_detect_params *det,
+                                  const fd_brief_params *brief, int cand_capacity, fd_keypoint *host_kp, int32_t *host_counts, uint8_t *host_desc,
+                                  int kp_capacity);
+
 /* ---- one large frame, row-tiled across GPUs -----------------------------------------
  * fd_set_tile declares the bound frames to be rows [row_offset, row_offset + rows) of an image full_rows tall, of which
  * the local rows [own_first_row, own_first_row + own_row_count) are this tile's own and the rest is halo (3 rows each side

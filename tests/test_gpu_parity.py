@@ -831,3 +831,33 @@ def test_hamming_matches_vs_numpy(ctx, torch_cuda):
             dist = lut[an[p_, q][None, :] ^ bn[p_, :nb]].sum(-1)
             assert o[p_, q, 0] == dist.argmin() and o[p_, q, 1] == dist.min()
             assert o[p_, q, 2] == (np.sort(dist)[1] if nb > 1 else -1)
+
+
+def test_one_call_host_to_host_equals_the_separate_calls(ctx, checker):
+    """fd_detect_describe_host (upload, detect, describe, downloads with one synchronisation) == the separate calls, for one frame (the
+    reference's call pattern), a few frames, pre-existing features, no descriptors, a host capacity below the device's, and an overflow."""
+    from feature_detector_b200.synth import synth
+    frames = np.stack([synth(752, 480, 500 + i) for i in range(3)])
+    det, brief = fd.DetectParams(fd.FAST, 10.0, 20, 200, fast_n=9), fd.BriefParams(256, 8)
+    for batch in (frames[:1], frames):
+        for existing in (None, [np.array([[100.0, 100.0], [400.0, 300.0]], np.float32)] * len(batch)):
+            ctx.set_existing_features(existing or [])
+            ctx.upload(batch)
+            ctx.detect(det)
+            ctx.describe_selected(brief)
+            kp_ref, cnt_ref = ctx.keypoints(200)
+            desc_ref = ctx.descriptors(200)
+            for cap in (200, 64):
+                kp, cnt, desc = ctx.detect_describe_host(batch, det, brief, cap)
+                if cap >= cnt_ref.max():
+                    assert np.array_equal(cnt, cnt_ref)
+                    for f in range(len(batch)):
+                        assert np.array_equal(kp[f, :cnt[f]], kp_ref[f, :cnt[f]]) and np.array_equal(desc[f, :cnt[f]], desc_ref[f, :cnt[f]])
+            kp, cnt, desc = ctx.detect_describe_host(batch, det, None, 200)
+            assert desc is None and np.array_equal(cnt, cnt_ref) and np.array_equal(kp[0, :cnt[0]], kp_ref[0, :cnt[0]])
+    ctx.set_existing_features([])
+    o = checker.detect(FAST, frames[0], 10.0, 20, 200, fast_n=9)
+    kp, cnt, _ = ctx.detect_describe_host(frames[0], det, brief, 200)
+    assert np.array_equal(np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1), o["features"])
+    with pytest.raises(fd.FdError):
+        ctx.detect_describe_host(frames[0], fd.DetectParams(fd.FAST, 0.1, 15, 200), brief, 200, cand_capacity=1000)
