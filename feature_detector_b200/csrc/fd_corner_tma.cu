@@ -258,21 +258,25 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                             if (col_owned[j] && v > p.thr && v > l && v > r && v > resp[cur][j] && v > rq[j]) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
-                            const uint32_t lo0 = (uint32_t(m + p.tile.row_offset) << 16) | uint32_t(c0);
+                            // Stage slots: a lane owns up to four candidates, so its count has three bits and the warp's exclusive prefix is
+                            // three ballots (one vote + one popcount per bit) instead of a vote per column; only the lanes that hold a
+                            // candidate then run the stores.
+                            const uint32_t cnt = uint32_t(__popc(mine));
                             const uint32_t lt = (1u << lane) - 1u;
-                            uint32_t base = n_staged;
+                            const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+                            if (mine != 0u) {
+                                uint32_t pos = n_staged + uint32_t(__popc(b0 & lt)) + 2u * uint32_t(__popc(b1 & lt)) + 4u * uint32_t(__popc(b2 & lt));
+                                const uint32_t lo0 = (uint32_t(m + p.tile.row_offset) << 16) | uint32_t(c0);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const bool on = (mine >> j) & 1u;
-                                const uint32_t bm = __ballot_sync(0xffffffffu, on);
-                                if (on) {
-                                    const uint32_t b = __float_as_uint(resp[p2][j]);
-                                    const uint32_t hi = b ^ ~(uint32_t(int32_t(b) >> 31) | 0x80000000u);   // ~float_to_ordered(b)
-                                    stage2[base + __popc(bm & lt)] = make_uint2(lo0 + uint32_t(j), hi);
+                                for (int j = 0; j < 4; ++j) {
+                                    if ((mine >> j) & 1u) {
+                                        const uint32_t b = __float_as_uint(resp[p2][j]);
+                                        const uint32_t hi = b ^ ~(uint32_t(int32_t(b) >> 31) | 0x80000000u);   // ~float_to_ordered(b)
+                                        stage2[pos++] = make_uint2(lo0 + uint32_t(j), hi);
+                                    }
                                 }
-                                base += __popc(bm);
                             }
-                            n_staged = base;
+                            n_staged += uint32_t(__popc(b0)) + 2u * uint32_t(__popc(b1)) + 4u * uint32_t(__popc(b2));
                             if (n_staged > CT_STAGE - 128) flush_stage();
                         }
                     }
