@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                             const float v = resp[p2][j];
                             const float l = (j == 0) ? left_in : resp[p2][j - 1];
                             const float r = (j == 3) ? right_in : resp[p2][j + 1];
-                            // v == 0 means "at or below threshold" (harris.cpp:130); strict 4-neighbour max (:131-132)
-                            if (col_owned[j] && v > p.thr && v > l && v > r && v > resp[cur][j] && v > rq[j]) mine |= 1u << j;
+                            // v == 0 means "at or below threshold" (harris.cpp:130); strict 4-neighbour max (:131-132) as one compare against
+                            // the largest neighbour (responses are finite, so the four strict compares and this one agree)
+                            const float big = fmaxf(fmaxf(l, r), fmaxf(resp[cur][j], rq[j]));
+                            if (col_owned[j] && v > p.thr && v > big) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
                             // Stage slots: a lane owns up to four candidates, so its count has three bits and the warp's exclusive prefix is
