@@ -37,7 +37,7 @@ def test_config1_fast_select_brief_752x480_batch(ctx, checker):
         for rep in range(1, 4):
             assert np.array_equal(cnt[:64], cnt[64 * rep:64 * rep + 64]) and np.array_equal(cand[:64], cand[64 * rep:64 * rep + 64])
             assert np.array_equal(kp[:64], kp[64 * rep:64 * rep + 64]) and np.array_equal(desc[:64], desc[64 * rep:64 * rep + 64])
-        for f in (0, 17, 63):
+        for f in range(0, 64, 3 if fast_n == 9 else 7):     # 22 / 10 of the 64 distinct frames against the checker, frame by frame
             o = checker.detect(FAST, base[f], 10.0, 20, 200, fast_n=fast_n)
             assert cand[f] == o["n_cand"] and np.array_equal(_feats(kp, cnt, f), o["features"]), (fast_n, f)
             ok, bits = checker.brief(base[f], o["features"], 256, 8)
@@ -51,7 +51,7 @@ def test_config2_shi_tomasi_top1000_1280x720(ctx, checker):
     ctx.upload(frames)
     ctx.detect(fd.DetectParams(fd.SHI_TOMAS, 40.0, 20, 1000), 0)
     kp, cnt = ctx.keypoints(1000)
-    for f in (0, 5):
+    for f in range(6):
         o = checker.detect(SHI_TOMAS, frames[f], 40.0, 20, 1000)
         cand = ctx.candidates(f)
         assert len(cand) == o["n_cand"]
@@ -89,7 +89,7 @@ def test_config4_lsd_field_1920x1080(ctx, checker):
     frames = np.stack([synth(1920, 1080, 900 + i) for i in range(3)])
     ctx.upload(frames)
     ctx.lsd_field(fd.LsdParams(20.0, 1))
-    for f in (0, 2):
+    for f in range(3):
         g = ctx.lsd_download(f)
         m = checker.lsd_map(frames[f])
         assert np.array_equal(g["norm"][:-1, :-1].view(np.uint32), m["norm"].view(np.uint32))
@@ -106,3 +106,18 @@ def test_config4_lsd_field_1920x1080(ctx, checker):
         cm = c.astype(np.int64) * 1080 + r                                           # and ties here in its push order
         assert np.all(np.diff(cm)[np.diff(seq) == 0] > 0)
         assert len(np.unique(idx)) == len(idx)
+
+
+def test_config3_second_frame_and_shi_tomasi_3840x2160(ctx, checker):
+    """configs[3] again on other frames: Harris and Shi-Tomasi candidate sets bitwise at 3840x2160 (the frames bench.py times)."""
+    from feature_detector_b200 import tiling
+    for idx, kind, ck, thr in ((1, fd.HARRIS, HARRIS, 30.0), (2, fd.SHI_TOMAS, SHI_TOMAS, 40.0)):
+        im = synth(3840, 2160, idx)
+        ctx.upload(im)
+        ctx.detect(fd.DetectParams(kind, thr, 20, 200))
+        kp, cnt = ctx.keypoints(200)
+        cand = ctx.candidates(0)
+        o = checker.detect(ck, im, thr, 20, 200)
+        assert len(cand) == o["n_cand"] and cnt[0] == len(o["features"])
+        want = np.sort(tiling.make_keys(o["cand_resp"], o["cand_xy"][:, 1], o["cand_xy"][:, 0]))
+        assert np.array_equal(np.sort(tiling.make_keys(cand["response"], cand["y"], cand["x"])), want)
