@@ -387,15 +387,27 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     __syncthreads();
                     m = *nxt_count;
                     if (m == 0u) break;
-                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                        const uint64_t key = nxt[i];
-                        const uint32_t xy = key_xy(key);
-                        const int c = cell_of(xy);
-                        if (uint64_t(cmin[c]) != key) continue;
-                        if (key < neighbour_min(cmin, pitch, c)) {
+                    if (m > uint32_t(n_cells)) {
+                        // more live candidates than cells (the first rounds): the cells' minima ARE the candidates that can win, so the
+                        // winners come from one pass over the cell grid in shared memory instead of a second pass over the live list
+                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+                            const uint64_t key = cmin[c];
+                            if (key == kDeadKey || key >= neighbour_min(cmin, pitch, c)) continue;
                             const uint32_t slot = atomicAdd(&s_kept, 1u);
                             if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                            cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
+                            cells[c] = key_xy(key);
+                        }
+                    } else {
+                        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                            const uint64_t key = nxt[i];
+                            const uint32_t xy = key_xy(key);
+                            const int c = cell_of(xy);
+                            if (uint64_t(cmin[c]) != key) continue;
+                            if (key < neighbour_min(cmin, pitch, c)) {
+                                const uint32_t slot = atomicAdd(&s_kept, 1u);
+                                if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
+                                cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
+                            }
                         }
                     }
                     __syncthreads();
