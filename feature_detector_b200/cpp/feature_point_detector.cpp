@@ -47,7 +47,6 @@ bool FeaturePointDetector::DetectGoodFeaturesBatch(const uint8_t *frames, int32_
     if (!EnsureContext()) return false;
     features.resize(size_t(n_frames));
 
-    if (fd_upload_frames(ctx_, frames, rows, cols, n_frames) != FD_OK) return Fail("fd_upload_frames");
 
     // existing features -> device mask (feature_point_detector.cpp:12-16)
     size_t max_pre = 0;
@@ -86,10 +85,11 @@ bool FeaturePointDetector::DetectGoodFeaturesBatch(const uint8_t *frames, int32_
     const int64_t px = int64_t(rows) * cols;
     int cand_capacity = (n_frames > 1 && px / 4 >= (1 << 16)) ? int(px / 4) : 0;
     for (;;) {
-        if (fd_detect(ctx_, &p, cand_capacity) != FD_OK) return Fail("fd_detect");
-        const fd_status st = fd_download_keypoints(ctx_, kp.data(), counts.data(), cap);
+        // upload, candidates, selection and the download of counts and keypoints as one call with one synchronisation: the reference's
+        // pattern is one frame per call, where every extra round trip to the device shows
+        const fd_status st = fd_detect_describe_host(ctx_, frames, rows, cols, n_frames, &p, nullptr, cand_capacity, kp.data(), counts.data(), nullptr, cap);
         if (st == FD_OK) break;
-        if (st != FD_ERR_CAPACITY || cand_capacity == 0) return Fail("fd_download_keypoints");
+        if (st != FD_ERR_CAPACITY || cand_capacity == 0) return Fail("fd_detect_describe_host");
         cand_capacity = 0;
     }
 

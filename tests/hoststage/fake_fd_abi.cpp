@@ -102,6 +102,17 @@ fd_status fd_download_keypoints(fd_context *ctx, fd_keypoint *host_kp, int32_t *
     return FD_OK;
 }
 
+// the one-call form the drop-in detector uses: the same three steps (descriptors are not asked for by the classes under test)
+fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames, const fd_detect_params *det,
+                                  const fd_brief_params *brief, int cand_capacity, fd_keypoint *host_kp, int32_t *host_counts, uint8_t *host_desc,
+                                  int kp_capacity) {
+    if (brief != nullptr || host_desc != nullptr) return FD_ERR_INVALID_ARGUMENT;
+    fd_status st = fd_upload_frames(ctx, host_frames, rows, cols, n_frames);
+    if (st == FD_OK) st = fd_detect(ctx, det, cand_capacity);
+    if (st == FD_OK) st = fd_download_keypoints(ctx, host_kp, host_counts, kp_capacity);
+    return st;
+}
+
 fd_status fd_download_candidates(fd_context *ctx, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out) {
     if (!ctx || frame != 0 || !n_out) return FD_ERR_INVALID_ARGUMENT;
     *n_out = int64_t(ctx->cand.size());
