@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/kernel_traffic.json from ncu reports: dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels bench.py's roofline
-objects name.  usage: make_traffic_json.py headline.ncu-rep configs.ncu-rep   (reports of `bench.py --no-extras` and `tools/prof_r2.py all`)"""
+objects name.  usage: make_traffic_json.py headline.ncu-rep config1.ncu-rep [config2.ncu-rep ...]   (reports of `bench.py --no-extras` and of `tools/prof_r2.py c2|c3|c4|headline`)"""
 import csv, io, json, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -23,8 +23,9 @@ def launches(rep):
     return out
 
 
-head, conf = launches(sys.argv[1]), launches(sys.argv[2])
-res = {"_source": {"headline": os.path.basename(sys.argv[1]), "configs": os.path.basename(sys.argv[2]),
+head = launches(sys.argv[1])
+conf = [l for rep in sys.argv[2:] for l in launches(rep)]
+res = {"_source": {"headline": os.path.basename(sys.argv[1]), "configs": [os.path.basename(r) for r in sys.argv[2:]],
                    "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none; the LAST captured launch of each kernel"}}
 
 
