@@ -11,6 +11,11 @@
 #   ncu          one --set full capture of the headline step's three kernels -> gpurun_out/prof_<tag>.ncu-rep, then read it HERE with
 #                tools/ncu_summary.py / tools/ncu_regions.py / tools/ncu_hotspots.py
 #   pipes        tools/microbench/pipes (issue rates of the instruction mixes the kernels are made of)
+#   stages       tools/stage_times.py: FAST / selection / BRIEF and the corner detectors stage by stage, one frame and 1024 frames
+#   profile-r2   the round-2 evidence set: launch list + ncu --set full of the headline step and of configs 2-4 (tools/prof_r2.py), one
+#                report per kernel group so that gpurun_out/ stays under gpurun's 64 MiB; read back HERE with tools/ncu_summary.py,
+#                tools/ncu_regions.py, tools/make_traffic_json.py (-> profiles/)
+#   tune F M V.. tools/tune_kernels.sh: rebuild file F with -DM=V on the box and time the stages (e.g. tune fd_brief.cu BRIEF_PERSISTENT 0 1)
 set -u
 mkdir -p gpurun_out
 what=${1:-tests}
@@ -30,5 +35,19 @@ case "$what" in
               python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_$tag.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_$tag.log ;;
   pipes)    make -s -C tools/microbench pipes 2>/dev/null || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/pipes tools/microbench/pipes.cu; \
             tools/microbench/pipes > gpurun_out/pipes.txt 2>&1; echo "rc=$?"; cat gpurun_out/pipes.txt ;;
-  *)        echo "unknown: $what"; sed -n 2,16p "$0"; exit 2 ;;
+  stages)   python tools/stage_times.py > gpurun_out/stage_times.json 2> gpurun_out/stage_times.err; echo "rc=$?"; cat gpurun_out/stage_times.json ;;
+  tune)     shift; tools/tune_kernels.sh "$@" ;;
+  profile-r2)
+            python bench.py --steps 2 --warmup 3 --no-extras > /dev/null 2>&1 && \
+            ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/ncu_r2_launches.log 2>&1; echo "launches rc=$?"
+            python bench.py --steps 1 --warmup 3 --no-extras > /dev/null 2>&1 && \
+            ncu --set full --clock-control none --import-source on -k regex:'fast_sparse_kernel|select_kernel|brief_kernel' -s 9 -c 3 -f -o gpurun_out/prof_r2_headline python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_r2_headline.log 2>&1; echo "headline rc=$?"
+            python tools/prof_r2.py all > /dev/null 2>&1 || { echo "tools/prof_r2.py failed without ncu"; exit 1; }
+            ncu --set full --clock-control none --import-source on -k regex:corner_tma_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_c2 python tools/prof_r2.py c2 > gpurun_out/ncu_r2_c2.log 2>&1
+            ncu --set full --clock-control none --import-source on -k regex:corner_tma_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_c3 python tools/prof_r2.py c3 > gpurun_out/ncu_r2_c3.log 2>&1
+            ncu --set full --clock-control none -k regex:gather_tiles_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_gather python tools/prof_r2.py c3 > gpurun_out/ncu_r2_gather.log 2>&1
+            ncu --set full --clock-control none --import-source on -k regex:'lsd_kernel|lsd_order_kernel|lsd_scatter_kernel' -s 3 -c 3 -f -o gpurun_out/prof_r2_c4 python tools/prof_r2.py c4 > gpurun_out/ncu_r2_c4.log 2>&1
+            ncu --set full --clock-control none -k regex:match_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_match python tools/prof_r2.py headline > gpurun_out/ncu_r2_match.log 2>&1
+            du -sh gpurun_out ;;
+  *)        echo "unknown: $what"; sed -n 2,22p "$0"; exit 2 ;;
 esac
