@@ -64,6 +64,10 @@ def main():
                     ctx.candidates(0)
                     ctx.describe_selected(fd.BriefParams(256, 8))
                     ctx.descriptors(max(int(prm.needed_feature_num), 1))
+                    ctx.match_selected()                                   # Hamming matching of consecutive frames (fd_match.cu)
+                    ctx.matches(max(int(prm.needed_feature_num), 1))
+                    if not with_pre:                                       # the one-call host-to-host form shares every buffer with the calls above
+                        ctx.detect_describe_host(frames, prm, fd.BriefParams(256, 8), max(int(prm.needed_feature_num), 1))
                 # dense outputs
                 resp = fenced((n, h, w), torch.float32)
                 score = fenced((n, h, w), torch.uint8)
