@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
         // candidates still alive (the first round kills most of them).  Beyond that -- FAST at the reference's default
         // threshold makes every pixel a candidate, and its raster-ordered ranking needs hundreds of rounds -- the admitted
         // candidates are grouped by cell once and a round costs work per CELL.
-        uint32_t prefix_k = by_prefix ? max(uint32_t(SELECT_PREFIX_MIN / 2), 8u * want_kept) : n;
+        uint32_t prefix_k = by_prefix ? max(uint32_t(SELECT_PREFIX_FIRST), 8u * want_kept) : n;
         constexpr int BINS = 1 << SELECT_HIST_BITS;
         if (by_prefix) {   // histogram of the top key bits, once
             for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0u;
