@@ -43,7 +43,7 @@ struct fd_context {
     int n_seg = 0;
     uint32_t seg_count_covered = 0;
 
-    DevBuf keys, keys_scratch, counts, flags, cells, alive, kept;
+    DevBuf keys, keys_scratch, counts, flags, cells, alive, kept, pre_hist, pre_keys;
     uint32_t cand_capacity = 0;
     bool have_candidates = false, candidates_sorted = false;
 
@@ -81,6 +81,7 @@ struct fd_context {
     int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
+    bool select_prepare = true;     // FD_B200_SELECT_PREPARE=0: testing knob, selection always builds its rank histogram and first range itself
 
     void *host_stage = nullptr;     // pinned staging block of fd_detect_describe_host
     size_t host_stage_bytes = 0;
@@ -544,8 +545,20 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.overflow_flag = static_cast<uint32_t *>(ctx->flags.ptr);
     a.mask = ctx->mask_view;
     a.xy_xor = xy_xor;
+    // Few frames whose slots admit many candidates (a 3840x2160 frame, the gathered tiles of one): one CTA per frame would stream over all
+    // of a frame's keys twice while most SMs idle, so the rank histogram and the first rank range are prepared by many CTAs per frame.
+    const bool prepare = fv.n_frames < 2 * ctx->sm_count && capacity > uint32_t(SELECT_PREFIX_MIN) && ctx->select_prepare;
+    if (prepare) {
+        const size_t hist_bytes = size_t(fv.n_frames) * 2048 * 4;
+        FD_TRY(reserve(ctx, ctx->pre_hist, hist_bytes + size_t(fv.n_frames) * 4));
+        FD_TRY(reserve(ctx, ctx->pre_keys, size_t(fv.n_frames) * capacity * 8));
+        FD_CUDA(ctx, cudaMemsetAsync(ctx->pre_hist.ptr, 0, hist_bytes + size_t(fv.n_frames) * 4, ctx->stream));
+        a.pre_hist = static_cast<uint32_t *>(ctx->pre_hist.ptr);
+        a.pre_counts = a.pre_hist + size_t(fv.n_frames) * 2048;
+        a.pre_keys = static_cast<uint64_t *>(ctx->pre_keys.ptr);
+    }
     FD_CUDA(ctx, launch_select(a, ctx->stream));
-    ctx->launches += (a.cand_capacity > a.cells_min) ? 2 : 1;   // the per-cell form is launched only when the capacity admits it
+    ctx->launches += ((a.cand_capacity > a.cells_min) ? 2 : 1) + (prepare ? 2 : 0);   // the per-cell form is launched only when the capacity admits it
     ctx->candidates_sorted = false;  // selection needs no global sort; fd_download_candidates orders its copy
     ctx->have_keypoints = true;
     ctx->select_frames = fv.n_frames;
@@ -586,6 +599,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     if (const char *env = std::getenv("FD_B200_FAST_DENSE")) ctx->force_dense_fast = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
+    if (const char *env = std::getenv("FD_B200_SELECT_PREPARE")) ctx->select_prepare = (env[0] != '0');
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -597,7 +611,7 @@ fd_status fd_destroy(fd_context *ctx) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->kp,
+    for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->pre_hist, &ctx->pre_keys, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
                       &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1], &ctx->matches})
         release(*b);

@@ -134,6 +134,9 @@ struct SelectArgs {
     int cells_in_smem;
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
+    uint32_t *pre_hist;             // optional (few frames, many candidates): n_frames * 2048 rank-histogram bins, zero on entry ...
+    uint64_t *pre_keys;             // ... n_frames slots of cand_capacity keys for the first rank range ...
+    uint32_t *pre_counts;           // ... and their fill, zero on entry (select_hist_kernel / select_admit_kernel)
     uint32_t xy_xor;                // 0, or 0xFFFFFFFF when the keys carry the complemented position (NN heat maps: among equal responses the later pixel first)
 };
 size_t select_cell_bytes(int cells_x, int cells_y);

@@ -55,6 +55,108 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(uint64_t *keys, cons
 }
 
 
+// The first histogram bin at which the running count reaches prefix_k: the batch admits the keys below the NEXT bin's first key.
+// One warp (BINS / 32 bins per lane); the lane that finds the bin writes the limit and the count of keys below it.
+__device__ __forceinline__ void warp_prefix_limit(const uint32_t *hist, uint32_t prefix_k, uint32_t n, uint64_t *out_limit, uint32_t *out_admit) {
+    constexpr int BINS = 1 << SELECT_HIST_BITS;
+    constexpr int PER = BINS / 32;
+    const int lane = lane_id();
+    uint32_t mine = 0u;
+#pragma unroll 4
+    for (int b = 0; b < PER; ++b) mine += hist[lane * PER + b];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t before = incl - mine;
+    if (before < prefix_k && incl >= prefix_k) {   // exactly one lane
+        uint32_t run = before;
+        int b = 0;
+#pragma unroll 1
+        for (; b < PER; ++b) {
+            run += hist[lane * PER + b];
+            if (run >= prefix_k) break;
+        }
+        const uint32_t bin = uint32_t(lane * PER + b);
+        *out_limit = (bin >= uint32_t(BINS - 1)) ? kDeadKey : (uint64_t(bin + 1u) << (64 - SELECT_HIST_BITS));
+        *out_admit = (bin >= uint32_t(BINS - 1)) ? n : run;
+    }
+}
+
+// How many candidates a frame still wants and how large its first rank range is (shared by the selection kernel and the kernels that
+// prepare its first range).
+__device__ __forceinline__ uint32_t select_want(const SelectArgs &p, int frame) {
+    const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
+    const uint32_t want = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;  // pushed, then tested: at least one
+    return min(want, uint32_t(p.kp_capacity));
+}
+__device__ __forceinline__ uint32_t select_first_range(uint32_t want_kept) { return max(uint32_t(SELECT_PREFIX_FIRST), 8u * want_kept); }
+
+// ---- few frames, many candidates (one 3840x2160 frame holds 5 x 10^5): the two passes that stream over ALL of a frame's keys -- the
+// rank histogram and the admission of the first rank range -- are what one CTA per frame spends its time on while most SMs idle.
+// These two kernels run them with many CTAs per frame; select_kernel then starts from the histogram and the admitted list.
+__global__ void __launch_bounds__(256) select_hist_kernel(const SelectArgs p) {
+    constexpr int BINS = 1 << SELECT_HIST_BITS;
+    __shared__ uint32_t hist[BINS];
+    const int frame = blockIdx.y;
+    const uint32_t n = min(p.cand_counts[frame], p.cand_capacity);
+    if (n <= uint32_t(SELECT_PREFIX_MIN)) return;
+    const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
+    const uint32_t per = ((n + gridDim.x - 1) / gridDim.x + 1023u) & ~1023u;   // whole trips of 4 x 256 keys
+    const uint32_t lo = blockIdx.x * per, hi = min(lo + per, n);
+    if (lo >= hi) return;
+    for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    for (uint32_t i0 = lo; i0 < hi; i0 += 4u * blockDim.x) {
+        uint64_t k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+            k4[u] = (i < hi) ? __ldg(keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+            const uint32_t bin = (i < hi) ? uint32_t(k4[u] >> (64 - SELECT_HIST_BITS)) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xFFFFFFFFu && lane_id() == __ffs(peers) - 1) atomicAdd(hist + bin, uint32_t(__popc(peers)));
+        }
+    }
+    __syncthreads();
+    uint32_t *out = p.pre_hist + int64_t(frame) * BINS;
+    for (int i = threadIdx.x; i < BINS; i += blockDim.x)
+        if (hist[i] != 0u) atomicAdd(out + i, hist[i]);
+}
+
+__global__ void __launch_bounds__(256) select_admit_kernel(const SelectArgs p) {
+    __shared__ uint64_t s_limit;
+    __shared__ uint32_t s_admit;
+    const int frame = blockIdx.y;
+    const uint32_t n = min(p.cand_counts[frame], p.cand_capacity);
+    if (n <= uint32_t(SELECT_PREFIX_MIN)) return;
+    const uint32_t prefix_k = select_first_range(select_want(p, frame));
+    if (prefix_k >= n) return;   // the first range is the whole frame: select_kernel walks the candidate slot itself
+    if (threadIdx.x < 32) warp_prefix_limit(p.pre_hist + int64_t(frame) * (1 << SELECT_HIST_BITS), prefix_k, n, &s_limit, &s_admit);
+    __syncthreads();
+    const uint64_t limit = s_limit;
+    const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
+    uint64_t *out = p.pre_keys + int64_t(frame) * p.cand_capacity;
+    const uint32_t per = ((n + gridDim.x - 1) / gridDim.x + 1023u) & ~1023u;
+    const uint32_t lo = blockIdx.x * per, hi = min(lo + per, n);
+    for (uint32_t i0 = lo; i0 < hi; i0 += 4u * blockDim.x) {
+        uint64_t k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+            k4[u] = (i < hi) ? __ldg(keys + i) : kDeadKey;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) list_push(k4[u] < limit, k4[u], out, p.pre_counts + frame);   // (the padding key is never below a limit)
+    }
+}
+
 // BY_CELLS picks the form of the rounds; a launch of one form leaves the frames of the other alone (the candidate counts live
 // on the device, so the host launches both forms whenever the capacity admits the per-cell one).
 template <bool BY_CELLS>
@@ -126,16 +228,19 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
         // rounds therefore run on rank ranges: first the keys up to the histogram bin (top 11 key bits) that holds the K-th
         // best key; if that keeps too few, the next range (K fourfold) is admitted against the points kept so far.  Exact,
         // and a 4K Harris frame with 5 x 10^5 candidates and needed = 200 touches a few thousand of them.
-        uint32_t want_kept = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;
-        want_kept = min(want_kept, uint32_t(p.kp_capacity));
+        const uint32_t want_kept = select_want(p, frame);
         const bool by_prefix = n > SELECT_PREFIX_MIN;
+        const bool prepared = by_prefix && p.pre_hist != nullptr;   // select_hist_kernel / select_admit_kernel ran for this launch
         // Two forms of the rounds, same result.  Up to SELECT_CELLS_MIN candidates: work per round proportional to the
         // candidates still alive (the first round kills most of them).  Beyond that -- FAST at the reference's default
         // threshold makes every pixel a candidate, and its raster-ordered ranking needs hundreds of rounds -- the admitted
         // candidates are grouped by cell once and a round costs work per CELL.
-        uint32_t prefix_k = by_prefix ? max(uint32_t(SELECT_PREFIX_FIRST), 8u * want_kept) : n;
+        uint32_t prefix_k = by_prefix ? select_first_range(want_kept) : n;
         constexpr int BINS = 1 << SELECT_HIST_BITS;
-        if (by_prefix) {   // histogram of the top key bits, once
+        if (prepared) {
+            for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = p.pre_hist[int64_t(frame) * BINS + i];
+            __syncthreads();
+        } else if (by_prefix) {   // histogram of the top key bits, once
             for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0u;
             __syncthreads();
             // neighbouring candidates mostly share a bin (FAST at a low threshold: 3 x 10^5 keys in a dozen bins), so each warp
@@ -164,37 +269,17 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
             uint64_t limit = kDeadKey;   // this batch admits lower <= key < limit
             uint32_t admitted = n;       // candidates with key < limit
             if (by_prefix && prefix_k < n) {
-                if (threadIdx.x < 32) {   // first bin at which the running count reaches prefix_k (one warp, BINS / 32 bins per lane)
-                    constexpr int PER = BINS / 32;
-                    uint32_t mine = 0u;
-#pragma unroll 4
-                    for (int b = 0; b < PER; ++b) mine += hist[threadIdx.x * PER + b];
-                    uint32_t incl = mine;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane_id() >= o) incl += v;
-                    }
-                    const uint32_t before = incl - mine;
-                    if (before < prefix_k && incl >= prefix_k) {   // exactly one lane
-                        uint32_t run = before;
-                        int b = 0;
-#pragma unroll 1
-                        for (; b < PER; ++b) {
-                            run += hist[threadIdx.x * PER + b];
-                            if (run >= prefix_k) break;
-                        }
-                        const uint32_t bin = threadIdx.x * PER + b;
-                        s_limit = (bin >= uint32_t(BINS - 1)) ? kDeadKey : (uint64_t(bin + 1u) << (64 - SELECT_HIST_BITS));
-                        s_admit = (bin >= uint32_t(BINS - 1)) ? n : run;
-                    }
-                }
+                if (threadIdx.x < 32) warp_prefix_limit(hist, prefix_k, n, &s_limit, &s_admit);
                 __syncthreads();
                 limit = s_limit;
                 admitted = s_admit;
                 __syncthreads();
             }
 
+            // the first rank range of a prepared frame was compacted by select_admit_kernel: walk that list instead of the whole slot
+            const bool from_list = prepared && batch == 0 && limit != kDeadKey;
+            const uint64_t *src = from_list ? p.pre_keys + int64_t(frame) * p.cand_capacity : keys;
+            const uint32_t src_n = from_list ? min(p.pre_counts[frame], p.cand_capacity) : n;
             if constexpr (BY_CELLS) {
                 // ---- admit: keys of this rank range that are not masked out and not covered by what is already kept ----
                 for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) cstart[i] = 0u;
@@ -205,12 +290,12 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(cstart + cell_of(key_xy(__ldg(keys + i))), 1u);
                 } else {
                     // four keys per thread per trip (loads in flight together); whole warps enter list_push together
-                    for (uint32_t i0 = 0; i0 < n; i0 += 4u * blockDim.x) {
+                    for (uint32_t i0 = 0; i0 < src_n; i0 += 4u * blockDim.x) {
                         uint64_t k4[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
-                            k4[u] = (i < n) ? __ldg(keys + i) : kDeadKey;
+                            k4[u] = (i < src_n) ? __ldg(src + i) : kDeadKey;
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -357,8 +442,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     s_count2[1] = 0u;
                 }
                 __syncthreads();
-                uint32_t m = n;               // live candidates entering the round
-                const uint64_t *cur = keys;   // round 0 walks the candidate slot itself
+                uint32_t m = src_n;           // live candidates entering the round
+                const uint64_t *cur = src;    // round 0 walks the candidate slot itself (or the prepared first range)
                 for (int round = 0;; ++round) {
                     uint64_t *nxt = (round & 1) ? list_b : list_a;
                     uint32_t *nxt_count = &s_count2[round & 1];
@@ -472,6 +557,11 @@ size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_
 
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(args);
+    if (args.pre_hist != nullptr) {   // few frames with room for many candidates each: histogram and first range by many CTAs per frame
+        const dim3 grid(unsigned(std::max(1, 4 * 148 / std::max(args.n_frames, 1))), unsigned(args.n_frames));
+        select_hist_kernel<<<grid, 256, 0, stream>>>(args);
+        select_admit_kernel<<<grid, 256, 0, stream>>>(args);
+    }
     // one CTA per frame: with fewer frames than SMs (the drop-in classes' one frame per call) a CTA has its SM to itself, and the
     // passes that stream over a frame's candidates are what its latency is made of
     const int threads = (args.cells_in_smem && args.n_frames > 148) ? SELECT_THREADS : SELECT_MAX_THREADS;

@@ -861,3 +861,46 @@ def test_one_call_host_to_host_equals_the_separate_calls(ctx, checker):
     assert np.array_equal(np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1), o["features"])
     with pytest.raises(fd.FdError):
         ctx.detect_describe_host(frames[0], fd.DetectParams(fd.FAST, 0.1, 15, 200), brief, 200, cand_capacity=1000)
+
+
+def test_prepared_first_rank_range_equals_in_kernel_one(checker):
+    """With few frames and many candidates the rank histogram and the first rank range are prepared by select_hist_kernel /
+    select_admit_kernel (many CTAs per frame); FD_B200_SELECT_PREPARE=0 makes the selection kernel stream over its frame itself.
+    Same keypoints either way -- both selection forms, one and several rank ranges, masks, and against the checker."""
+    import os
+    from feature_detector_b200.synth import synth
+    os.environ["FD_B200_SELECT_PREPARE"] = "0"
+    try:
+        plain = fd.Context(0)
+    finally:
+        del os.environ["FD_B200_SELECT_PREPARE"]
+    prepared = fd.Context(0)
+    try:
+        rng = np.random.default_rng(23)
+        batches = [np.stack([synth(752, 480, 40 + i) for i in range(3)]), synth(1920, 1080, 3)[None], rng.integers(0, 256, (2, 300, 400), dtype=np.uint8)]
+        cases = [(fd.HARRIS, 30.0, 20, 200, 12), (fd.HARRIS, 0.1, 5, 3000, 12), (fd.FAST, 0.1, 15, 200, 12), (fd.FAST, 0.1, 15, 5000, 9),
+                 (fd.SHI_TOMAS, 0.1, 20, 50, 12), (fd.FAST, 10.0, 20, 200, 9)]
+        for frames in batches:
+            h, w = frames.shape[1:]
+            existing = [np.stack([rng.integers(0, w, 9), rng.integers(0, h, 9)], 1).astype(np.float32) for _ in range(len(frames))]
+            for kind, thr, d, n, fast_n in cases:
+                for with_existing in (False, True):
+                    out = []
+                    for c in (plain, prepared):
+                        c.upload(frames)
+                        c.set_existing_features(existing if with_existing else [])
+                        c.detect(fd.DetectParams(kind, thr, d, n, fast_n=fast_n), 0)
+                        out.append(c.keypoints(max(n, 1)))
+                    assert np.array_equal(out[0][1], out[1][1]), (kind, thr, d, n, with_existing)
+                    for f in range(len(frames)):
+                        k = out[0][1][f]
+                        assert np.array_equal(out[0][0][f, :k], out[1][0][f, :k]), (kind, thr, d, n, with_existing, f)
+        prepared.set_existing_features([])
+        prepared.upload(batches[1])
+        prepared.detect(fd.DetectParams(fd.FAST, 0.1, 15, 300, fast_n=12), 0)
+        kp, cnt = prepared.keypoints(300)
+        o = checker.detect(FAST, batches[1][0], 0.1, 15, 300, fast_n=12)
+        assert np.array_equal(np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1).astype(np.float32), o["features"])
+    finally:
+        plain.close()
+        prepared.close()
