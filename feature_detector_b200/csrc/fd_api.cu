@@ -547,7 +547,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.xy_xor = xy_xor;
     // Few frames whose slots admit many candidates (a 3840x2160 frame, the gathered tiles of one): one CTA per frame would stream over all
     // of a frame's keys twice while most SMs idle, so the rank histogram and the first rank range are prepared by many CTAs per frame.
-    const bool prepare = fv.n_frames < 2 * ctx->sm_count && capacity > uint32_t(SELECT_PREFIX_MIN) && ctx->select_prepare;
+    const bool prepare = fv.n_frames < 2 * ctx->sm_count && capacity > uint32_t(SELECT_CELLS_MIN) && ctx->select_prepare;   // (two more launches: not worth it for slots a CTA streams in a few trips)
     if (prepare) {
         const size_t hist_bytes = size_t(fv.n_frames) * 2048 * 4;
         FD_TRY(reserve(ctx, ctx->pre_hist, hist_bytes + size_t(fv.n_frames) * 4));
