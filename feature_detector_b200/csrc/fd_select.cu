@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     uint32_t *cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     uint32_t *cstart = cells + n_cells;                                 // n_cells + 1 entries
     uint16_t *knew = reinterpret_cast<uint16_t *>(cstart + n_cells + 1);
-    __shared__ uint32_t s_kept, s_count, s_count2[2], s_admit, s_work, s_warp[32];
+    __shared__ uint32_t s_kept, s_count, s_count2[2], s_admit, s_work, s_active, s_warp[32];
     __shared__ uint64_t s_limit;
     // s_sort doubles as the 2048-bin (8 KiB) histogram of the rank-prefix search below
     __shared__ uint64_t s_sort[SELECT_SORT_SMEM];
@@ -343,6 +343,15 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                         atomicMin(cmin + c, static_cast<unsigned long long>(key));
                     }
                     __syncthreads();
+                    // the cells that hold candidates: a fine grid (19 000 cells of a 3840x2160 frame) is mostly empty once the rounds run on
+                    // a rank range of a few thousand keys, and the rounds below only walk this list
+                    uint32_t *active = work + p.cand_capacity;   // second half of the list storage (never more cells than candidates)
+                    if (threadIdx.x == 0) s_active = 0u;
+                    __syncthreads();
+                    for (int c = 1 + threadIdx.x; c < n_cells; c += blockDim.x)
+                        if (cstart[c] != cstart[c - 1]) active[atomicAdd(&s_active, 1u)] = uint32_t(c);
+                    __syncthreads();
+                    const int n_active = int(s_active);
 
                     // ---- rounds ----
                     const int sub = lane_id() & 7, group = int(threadIdx.x >> 3), n_groups = int(blockDim.x >> 3);
@@ -354,9 +363,10 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             __syncthreads();
                         }
                         if (threadIdx.x == 0) s_work = 0u;
-                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+                        for (int a = threadIdx.x; a < n_active; a += blockDim.x) {
+                            const int c = int(active[a]);
                             const uint64_t mine = cmin[c];
-                            if (mine == kDeadKey) continue;   // border cells and cells without live candidates
+                            if (mine == kDeadKey) continue;   // no live candidate left in the cell
                             if (mine < neighbour_min(cmin, pitch, c)) {
                                 const uint32_t slot = atomicAdd(&s_kept, 1u);
                                 if (slot < uint32_t(p.kept_capacity)) kept[slot] = mine;
@@ -367,7 +377,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                         __syncthreads();
                         // cells with live candidates next to a point kept this round go on the work list
                         bool alive = false;
-                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+                        for (int a = threadIdx.x; a < n_active; a += blockDim.x) {
+                            const int c = int(active[a]);
                             if (cmin[c] == kDeadKey) continue;
                             bool fresh = false;
 #pragma unroll
