@@ -19,10 +19,17 @@
 //     B  a live candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no
 //        live better-ranked candidate within d, so the sequential walk would keep it: it is kept now, written
 //        to the frame's kept list and to the cell grid.  All such candidates of a round are independent.
-//     Work per round is proportional to the candidates still alive, and the first round kills most of them.
+//     Work per round is proportional to the candidates still alive, and the first round kills most of them.  While live
+//     candidates outnumber cells (the first rounds) step B is one pass over the cell grid in shared memory -- the cells'
+//     minima ARE the candidates that can win -- instead of a second pass over the live list in global memory.
 //   per cell (select_kernel<true>, frames with more candidates: FAST at the reference's default threshold, 4K Harris)
 //     the admitted candidates are grouped by cell once; a cell whose best live candidate beats the best of the 8 cells
-//     around it keeps it; cells next to a fresh point drop the candidates it covers and recompute their best.
+//     around it keeps it; cells next to a fresh point drop the candidates it covers and recompute their best.  The rounds
+//     walk the list of cells that hold candidates, not the grid.
+// With more than SELECT_PREFIX_MIN candidates the rounds run on rank ranges (a histogram of the top key bits picks them).
+// select_hist_kernel / select_admit_kernel: few frames with many candidates each (a batch of 3840x2160 frames, the gathered
+// tiles of one) would leave most SMs idle while each frame's one CTA streams over all of its keys twice; these two kernels
+// build the histogram and compact the first rank range with many CTAs per frame, and select_kernel starts from their output.
 // The kept list is then sorted by key (a few hundred entries, bitonic in shared memory) and cut at
 // max(needed - existing, 1) -- the reference tests the count AFTER each push (:67-68), so needed = 0 still
 // yields one feature.  Pre-existing features need no handling here: their squares were already masked out of
