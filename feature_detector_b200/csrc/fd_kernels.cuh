@@ -94,7 +94,10 @@ struct CornerArgs {
 };
 cudaError_t launch_corner(const CornerArgs &args, int grid, cudaStream_t stream);
 // TMA form (fd_corner_tma.cu): needs a 3-D TMA map of the frames with a 160 x CORNER_TMA_GROUP_ROWS x 1 box, and no mask.
-constexpr int CORNER_TMA_THREADS = 512;
+#ifndef FD_CORNER_TMA_THREADS
+#define FD_CORNER_TMA_THREADS 512   // 640 / 768 (102 / 85 registers per thread) were measured on B200: see DESIGN.md section 8
+#endif
+constexpr int CORNER_TMA_THREADS = FD_CORNER_TMA_THREADS;
 constexpr int CORNER_TMA_GROUP_ROWS = 12;
 size_t corner_tma_smem_bytes();
 cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, int grid, cudaStream_t stream);
