@@ -197,6 +197,38 @@ int main(int argc, char **argv) {
             std::printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", double(lines[i][0]), double(lines[i][1]), double(lines[i][2]), double(lines[i][3]));
         std::printf("]}");
     }
+    {   // DetectGoodFeaturesBatch (an addition: many frames per call): three frames, each with its own pre-existing features, must give what
+        // three single-frame calls give -- Harris at the demo settings, and FAST at the reference's default threshold, whose ~343 000
+        // candidates per frame overflow the batch's first, bounded candidate slots and make the call run again with full ones
+        std::vector<uint8_t> frames(size_t(3) * rows * cols);
+        for (int f = 0; f < 3; ++f)
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols; ++c) frames[(size_t(f) * rows + r) * cols + c] = buf[size_t((r + 7 * f) % rows) * cols + (c + 13 * f) % cols];
+        bool all_ok = true, all_equal = true;
+        size_t n_total = 0;
+        for (int which = 0; which < 2; ++which) {
+            FeaturePointHarrisDetector harris;
+            FeaturePointFastDetector fast;
+            FeaturePointDetector &det = which == 0 ? static_cast<FeaturePointDetector &>(harris) : static_cast<FeaturePointDetector &>(fast);
+            det.options().kMinFeatureDistance = which == 0 ? 20 : 15;
+            det.options().kMinValidResponse = which == 0 ? 30.0f : 0.1f;
+            std::vector<std::vector<Vec2>> batch(3);
+            batch[1].emplace_back(Vec2(100.0f, 100.0f));
+            batch[2].emplace_back(Vec2(300.0f, 200.0f));
+            batch[2].emplace_back(Vec2(50.5f, 400.25f));
+            std::vector<std::vector<Vec2>> single = batch;
+            all_ok = det.DetectGoodFeaturesBatch(frames.data(), rows, cols, 3, 200, batch) && all_ok;
+            for (int f = 0; f < 3; ++f) {
+                GrayImage one(frames.data() + size_t(f) * rows * cols, rows, cols, false);
+                all_ok = det.DetectGoodFeatures(one, 200, single[f]) && all_ok;
+                all_equal = all_equal && single[f].size() == batch[f].size();
+                for (size_t i = 0; all_equal && i < single[f].size(); ++i) all_equal = single[f][i].x() == batch[f][i].x() && single[f][i].y() == batch[f][i].y();
+                n_total += batch[f].size();
+            }
+        }
+        std::printf(",\n \"batch_of_three\": {\"ok\": %s, \"equals_single_frame_calls\": %s, \"n_features\": %zu}", all_ok ? "true" : "false",
+                    all_equal ? "true" : "false", n_total);
+    }
     if (argc >= 8) {   // NN post-processing: <heat map f32 file> <descriptor volume f32 file> <channels> <pre-existing features>
         const int channels = std::atoi(argv[6]), n_pre = std::atoi(argv[7]);
         auto read_floats = [](const char *path, size_t n, std::vector<float> &v) {

@@ -130,6 +130,14 @@ def _check_nn(dropin_output, checker):
 
 
 @pytest.mark.gpu
+def test_dropin_batch_call_equals_single_frame_calls(dropin_output):
+    """DetectGoodFeaturesBatch on three frames with per-frame pre-existing features == three DetectGoodFeatures calls, for Harris and for
+    FAST at the reference's default threshold (whose candidate count overflows the batch's bounded first slots: the call runs again)."""
+    b = dropin_output["batch_of_three"]
+    assert b["ok"] is True and b["equals_single_frame_calls"] is True and b["n_features"] > 600, b
+
+
+@pytest.mark.gpu
 def test_dropin_replays_reference_demos(dropin_output, kat, image_png, checker):
     _check_demos(dropin_output, kat, image_png, checker)
 

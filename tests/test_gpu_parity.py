@@ -904,3 +904,24 @@ def test_prepared_first_rank_range_equals_in_kernel_one(checker):
     finally:
         plain.close()
         prepared.close()
+
+
+def test_describe_selected_refuses_keypoints_of_other_frames(ctx, torch_cuda):
+    """Keypoints selected from caller-supplied candidate keys (row tiles, gathered keys) or from a heat map do not belong to the bound
+    frames -- another frame count, another coordinate frame -- so fd_describe_selected answers FD_ERR_NOT_READY instead of reading the
+    keypoint slots of a different selection out of bounds."""
+    from feature_detector_b200.synth import synth
+    torch = torch_cuda
+    frames = np.stack([synth(320, 200, i) for i in range(3)])
+    ctx.upload(frames)
+    ctx.set_existing_features([])
+    prm = fd.DetectParams(fd.HARRIS, 30.0, 20, 50)
+    ctx.detect(prm)
+    ctx.describe_selected(fd.BriefParams(256, 8))                      # fine: the selection covered the bound frames
+    keys_ptr, counts_ptr, cap = ctx.device_candidates()
+    ctx.select_candidates(prm, keys_ptr, counts_ptr, cap, 200, 320, 1)  # one frame's worth of external keys
+    with pytest.raises(fd.FdError) as e:
+        ctx.describe_selected(fd.BriefParams(256, 8))
+    assert e.value.status == 6                                          # FD_ERR_NOT_READY
+    ctx.detect(prm)
+    ctx.describe_selected(fd.BriefParams(256, 8))                      # and usable again after a detect over the bound frames
