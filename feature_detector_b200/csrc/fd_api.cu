@@ -12,6 +12,7 @@
 #include <cuda.h>
 
 #include "../../include/fd_b200.h"
+#include "fd_internal.h"
 #include "fd_kernels.cuh"
 
 using namespace fdb;
@@ -504,8 +505,13 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
 
 // Greedy selection over candidate keys of n_frames frames of rows x cols pixels (the context's own candidates, or keys
 // gathered from the row tiles of one frame).
+struct SelectExtras {   // row tiles (fd_tiled.cu): see fd_internal.h
+    const fd_select_prefilter *first_range = nullptr;   // run on the gathered first rank ranges only, flag what needs more
+    const uint8_t *only_flagged = nullptr;               // run for flagged frames only (and never through the preparation kernels)
+};
+
 fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int cols, int n_frames, uint64_t *keys, const uint32_t *counts,
-                     uint32_t capacity, uint32_t xy_xor = 0u) {
+                     uint32_t capacity, uint32_t xy_xor = 0u, const SelectExtras *ex = nullptr) {
     struct { int rows, cols, n_frames; } fv = {rows, cols, n_frames};
     const int kp_cap = int(std::max<uint32_t>(1u, std::min<uint32_t>(p->needed_feature_num, 1u << 20)));
     ctx->kp_capacity = kp_cap;
@@ -547,7 +553,18 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     a.xy_xor = xy_xor;
     // Few frames whose slots admit many candidates (a 3840x2160 frame, the gathered tiles of one): one CTA per frame would stream over all
     // of a frame's keys twice while most SMs idle, so the rank histogram and the first rank range are prepared by many CTAs per frame.
-    const bool prepare = fv.n_frames < 2 * ctx->sm_count && capacity > uint32_t(SELECT_CELLS_MIN) && ctx->select_prepare;   // (two more launches: not worth it for slots a CTA streams in a few trips)
+    bool prepare = fv.n_frames < 2 * ctx->sm_count && capacity > uint32_t(SELECT_CELLS_MIN) && ctx->select_prepare;   // (two more launches: not worth it for slots a CTA streams in a few trips)
+    if (ex != nullptr) {
+        prepare = false;
+        a.only_flagged = ex->only_flagged;
+        if (ex->first_range != nullptr) {
+            a.pre_hist = ex->first_range->hist;
+            a.pre_keys = ex->first_range->pre_keys;
+            a.pre_counts = ex->first_range->pre_counts;
+            a.pre_capacity = ex->first_range->pre_capacity;
+            a.need_more = ex->first_range->need_more;
+        }
+    }
     if (prepare) {
         const size_t hist_bytes = size_t(fv.n_frames) * 2048 * 4;
         FD_TRY(reserve(ctx, ctx->pre_hist, hist_bytes + size_t(fv.n_frames) * 4));
@@ -556,6 +573,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
         a.pre_hist = static_cast<uint32_t *>(ctx->pre_hist.ptr);
         a.pre_counts = a.pre_hist + size_t(fv.n_frames) * 2048;
         a.pre_keys = static_cast<uint64_t *>(ctx->pre_keys.ptr);
+        a.pre_capacity = capacity;
     }
     FD_CUDA(ctx, launch_select(a, ctx->stream));
     ctx->launches += ((a.cand_capacity > a.cells_min) ? 2 : 1) + (prepare ? 2 : 0);   // the per-cell form is launched only when the capacity admits it
@@ -804,6 +822,35 @@ fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, 
     ctx->select_frames = n_frames;
     return run_select(ctx, params, rows, cols, n_frames, dev_keys, dev_counts, capacity);
 }
+
+}  // extern "C"
+
+fd_status fd_internal_select_first_range(fd_context *ctx, const fd_detect_params *params, const fd_select_prefilter *pf, int rows, int cols, int n_frames) {
+    if (!ctx || !pf || rows <= 0 || cols <= 0 || n_frames <= 0) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_internal_select_first_range: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(check_params(ctx, params));
+    FD_TRY(reserve(ctx, ctx->flags, 16));
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->flags.ptr, 0, 16, ctx->stream));
+    ctx->mask_view = MaskView{};
+    SelectExtras ex;
+    ex.first_range = pf;
+    // the full key slots are not read in this mode: the candidate pointer only has to be non-null
+    FD_TRY(run_select(ctx, params, rows, cols, n_frames, pf->pre_keys, pf->total_counts, pf->total_capacity, 0u, &ex));
+    return FD_OK;
+}
+
+fd_status fd_internal_select_flagged(fd_context *ctx, const fd_detect_params *params, uint64_t *dev_keys, const uint32_t *dev_counts, uint32_t capacity,
+                                     const uint8_t *flags, int rows, int cols, int n_frames) {
+    if (!ctx || !dev_keys || !dev_counts || !flags) return fail(ctx, FD_ERR_INVALID_ARGUMENT, "fd_internal_select_flagged: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_TRY(check_params(ctx, params));
+    ctx->mask_view = MaskView{};
+    SelectExtras ex;
+    ex.only_flagged = flags;
+    return run_select(ctx, params, rows, cols, n_frames, dev_keys, dev_counts, capacity, 0u, &ex);
+}
+
+extern "C" {
 
 fd_status fd_candidate_counts(fd_context *ctx, int32_t *host_counts) {
     if (!ctx || !host_counts) return FD_ERR_INVALID_ARGUMENT;

@@ -140,10 +140,20 @@ struct SelectArgs {
     uint32_t *pre_hist;             // optional (few frames, many candidates): n_frames * 2048 rank-histogram bins, zero on entry ...
     uint64_t *pre_keys;             // ... n_frames slots of cand_capacity keys for the first rank range ...
     uint32_t *pre_counts;           // ... and their fill, zero on entry (select_hist_kernel / select_admit_kernel)
+    uint32_t pre_capacity;          // slots per frame of pre_keys
+    // row tiles (fd_tiled.cu): the histogram is built per tile whatever its count, the first range's limit is handed to the tiles ...
+    int hist_always;                // select_hist_kernel: also frames of SELECT_PREFIX_MIN candidates or fewer
+    const uint64_t *ext_limits;     // select_admit_kernel: per frame, admit keys below this (0: leave the frame alone) instead of deriving it
+    // ... and the selection runs on the gathered first ranges alone; a frame that needs more than that is flagged, not finished
+    uint8_t *need_more;             // select_kernel, first-range mode: set to 1 for frames it could not finish (untouched otherwise)
+    const uint8_t *only_flagged;    // select_kernel: skip frames whose flag is 0
     uint32_t xy_xor;                // 0, or 0xFFFFFFFF when the keys carry the complemented position (NN heat maps: among equal responses the later pixel first)
 };
 size_t select_cell_bytes(int cells_x, int cells_y);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
+// The two preparation kernels on their own (fd_tiled.cu runs them on the tiles' devices): grid = chunks x n_frames.
+cudaError_t launch_select_hist(const SelectArgs &args, cudaStream_t stream);
+cudaError_t launch_select_admit(const SelectArgs &args, cudaStream_t stream);
 
 // ---- kernel 4: steered BRIEF --------------------------------------------------------------------
 struct BriefArgs {

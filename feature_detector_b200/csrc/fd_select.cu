@@ -62,45 +62,6 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(uint64_t *keys, cons
 }
 
 
-// The first histogram bin at which the running count reaches prefix_k: the batch admits the keys below the NEXT bin's first key.
-// One warp (BINS / 32 bins per lane); the lane that finds the bin writes the limit and the count of keys below it.
-__device__ __forceinline__ void warp_prefix_limit(const uint32_t *hist, uint32_t prefix_k, uint32_t n, uint64_t *out_limit, uint32_t *out_admit) {
-    constexpr int BINS = 1 << SELECT_HIST_BITS;
-    constexpr int PER = BINS / 32;
-    const int lane = lane_id();
-    uint32_t mine = 0u;
-#pragma unroll 4
-    for (int b = 0; b < PER; ++b) mine += hist[lane * PER + b];
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const uint32_t before = incl - mine;
-    if (before < prefix_k && incl >= prefix_k) {   // exactly one lane
-        uint32_t run = before;
-        int b = 0;
-#pragma unroll 1
-        for (; b < PER; ++b) {
-            run += hist[lane * PER + b];
-            if (run >= prefix_k) break;
-        }
-        const uint32_t bin = uint32_t(lane * PER + b);
-        *out_limit = (bin >= uint32_t(BINS - 1)) ? kDeadKey : (uint64_t(bin + 1u) << (64 - SELECT_HIST_BITS));
-        *out_admit = (bin >= uint32_t(BINS - 1)) ? n : run;
-    }
-}
-
-// How many candidates a frame still wants and how large its first rank range is (shared by the selection kernel and the kernels that
-// prepare its first range).
-__device__ __forceinline__ uint32_t select_want(const SelectArgs &p, int frame) {
-    const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
-    const uint32_t want = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;  // pushed, then tested: at least one
-    return min(want, uint32_t(p.kp_capacity));
-}
-__device__ __forceinline__ uint32_t select_first_range(uint32_t want_kept) { return max(uint32_t(SELECT_PREFIX_FIRST), 8u * want_kept); }
-
 // ---- few frames, many candidates (one 3840x2160 frame holds 5 x 10^5): the two passes that stream over ALL of a frame's keys -- the
 // rank histogram and the admission of the first rank range -- are what one CTA per frame spends its time on while most SMs idle.
 // These two kernels run them with many CTAs per frame; select_kernel then starts from the histogram and the admitted list.
@@ -109,7 +70,7 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const SelectArgs p) {
     __shared__ uint32_t hist[BINS];
     const int frame = blockIdx.y;
     const uint32_t n = min(p.cand_counts[frame], p.cand_capacity);
-    if (n <= uint32_t(SELECT_PREFIX_MIN)) return;
+    if (n <= uint32_t(SELECT_PREFIX_MIN) && !p.hist_always) return;
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
     const uint32_t per = ((n + gridDim.x - 1) / gridDim.x + 1023u) & ~1023u;   // whole trips of 4 x 256 keys
     const uint32_t lo = blockIdx.x * per, hi = min(lo + per, n);
@@ -142,14 +103,20 @@ __global__ void __launch_bounds__(256) select_admit_kernel(const SelectArgs p) {
     __shared__ uint32_t s_admit;
     const int frame = blockIdx.y;
     const uint32_t n = min(p.cand_counts[frame], p.cand_capacity);
-    if (n <= uint32_t(SELECT_PREFIX_MIN)) return;
-    const uint32_t prefix_k = select_first_range(select_want(p, frame));
-    if (prefix_k >= n) return;   // the first range is the whole frame: select_kernel walks the candidate slot itself
-    if (threadIdx.x < 32) warp_prefix_limit(p.pre_hist + int64_t(frame) * (1 << SELECT_HIST_BITS), prefix_k, n, &s_limit, &s_admit);
-    __syncthreads();
-    const uint64_t limit = s_limit;
+    uint64_t limit;
+    if (p.ext_limits != nullptr) {   // a row tile: the limit comes from all tiles' histograms together
+        limit = p.ext_limits[frame];
+        if (limit == 0ull) return;
+    } else {
+        if (n <= uint32_t(SELECT_PREFIX_MIN)) return;
+        const uint32_t prefix_k = select_first_range(select_want(p, frame));
+        if (prefix_k >= n) return;   // the first range is the whole frame: select_kernel walks the candidate slot itself
+        if (threadIdx.x < 32) warp_prefix_limit(p.pre_hist + int64_t(frame) * (1 << SELECT_HIST_BITS), prefix_k, n, &s_limit, &s_admit);
+        __syncthreads();
+        limit = s_limit;
+    }
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
-    uint64_t *out = p.pre_keys + int64_t(frame) * p.cand_capacity;
+    uint64_t *out = p.pre_keys + int64_t(frame) * p.pre_capacity;
     const uint32_t per = ((n + gridDim.x - 1) / gridDim.x + 1023u) & ~1023u;
     const uint32_t lo = blockIdx.x * per, hi = min(lo + per, n);
     for (uint32_t i0 = lo; i0 < hi; i0 += 4u * blockDim.x) {
@@ -191,6 +158,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     if (count > p.cand_capacity && threadIdx.x == 0) atomicExch(p.overflow_flag, 1u);
     const uint32_t n = min(count, p.cand_capacity);
     if ((n > p.cells_min) != BY_CELLS) return;
+    if (p.only_flagged != nullptr && p.only_flagged[frame] == 0) return;   // finished by the first-range launch
+    const bool first_range_only = p.need_more != nullptr;   // row tiles: only the gathered first rank range is at hand
     const uint64_t *keys = p.cand_keys + int64_t(frame) * p.cand_capacity;
     // binned: the admitted candidates grouped by cell; admitted: the same keys in arrival order, before grouping
     uint64_t *binned = p.live_scratch + int64_t(frame) * p.cand_capacity * 2;
@@ -217,6 +186,10 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
 
+    if (first_range_only && (d < 0 || n <= uint32_t(SELECT_PREFIX_MIN))) {   // needs the frame's full key slot: leave it to the flagged launch
+        if (threadIdx.x == 0) p.need_more[frame] = 1;
+        return;
+    }
     if (d < 0) {
         // no suppression at all (DrawRectangleInMask clears nothing for a negative distance): everything is kept
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
@@ -285,8 +258,12 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
 
             // the first rank range of a prepared frame was compacted by select_admit_kernel: walk that list instead of the whole slot
             const bool from_list = prepared && batch == 0 && limit != kDeadKey;
-            const uint64_t *src = from_list ? p.pre_keys + int64_t(frame) * p.cand_capacity : keys;
-            const uint32_t src_n = from_list ? min(p.pre_counts[frame], p.cand_capacity) : n;
+            if (first_range_only && !from_list) {   // (uniform over the CTA) no compacted range, or it did not yield enough points
+                if (threadIdx.x == 0) p.need_more[frame] = 1;
+                return;
+            }
+            const uint64_t *src = from_list ? p.pre_keys + int64_t(frame) * p.pre_capacity : keys;
+            const uint32_t src_n = from_list ? min(p.pre_counts[frame], p.pre_capacity) : n;
             if constexpr (BY_CELLS) {
                 // ---- admit: keys of this rank range that are not masked out and not covered by what is already kept ----
                 for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) cstart[i] = 0u;
@@ -573,12 +550,25 @@ size_t select_cell_bytes(int cells_x, int cells_y) {   // cmin (8) + kept point 
 
 size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_cell_bytes(a.cells_x, a.cells_y) : 0; }
 
+namespace {
+dim3 prepare_grid(int n_frames) { return dim3(unsigned(std::max(1, 4 * 148 / std::max(n_frames, 1))), unsigned(n_frames)); }
+}  // namespace
+
+cudaError_t launch_select_hist(const SelectArgs &args, cudaStream_t stream) {
+    select_hist_kernel<<<prepare_grid(args.n_frames), 256, 0, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_admit(const SelectArgs &args, cudaStream_t stream) {
+    select_admit_kernel<<<prepare_grid(args.n_frames), 256, 0, stream>>>(args);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(args);
-    if (args.pre_hist != nullptr) {   // few frames with room for many candidates each: histogram and first range by many CTAs per frame
-        const dim3 grid(unsigned(std::max(1, 4 * 148 / std::max(args.n_frames, 1))), unsigned(args.n_frames));
-        select_hist_kernel<<<grid, 256, 0, stream>>>(args);
-        select_admit_kernel<<<grid, 256, 0, stream>>>(args);
+    if (args.pre_hist != nullptr && args.need_more == nullptr) {   // few frames with room for many candidates each: histogram and first range by many CTAs per frame
+        select_hist_kernel<<<prepare_grid(args.n_frames), 256, 0, stream>>>(args);
+        select_admit_kernel<<<prepare_grid(args.n_frames), 256, 0, stream>>>(args);
     }
     // one CTA per frame: with fewer frames than SMs (the drop-in classes' one frame per call) a CTA has its SM to itself, and the
     // passes that stream over a frame's candidates are what its latency is made of

@@ -84,5 +84,45 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
 
 constexpr int SELECT_HIST_BITS = 11;   // rank-prefix histogram over the top key bits: sign, exponent, two mantissa bits
 
+// The first histogram bin at which the running count reaches prefix_k: the batch admits the keys below the NEXT bin's first key.
+// One warp (BINS / 32 bins per lane); the lane that finds the bin writes the limit and the count of keys below it.
+__device__ __forceinline__ void warp_prefix_limit(const uint32_t *hist, uint32_t prefix_k, uint32_t n, uint64_t *out_limit, uint32_t *out_admit) {
+    constexpr int BINS = 1 << SELECT_HIST_BITS;
+    constexpr int PER = BINS / 32;
+    const int lane = lane_id();
+    uint32_t mine = 0u;
+#pragma unroll 4
+    for (int b = 0; b < PER; ++b) mine += hist[lane * PER + b];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t before = incl - mine;
+    if (before < prefix_k && incl >= prefix_k) {   // exactly one lane
+        uint32_t run = before;
+        int b = 0;
+#pragma unroll 1
+        for (; b < PER; ++b) {
+            run += hist[lane * PER + b];
+            if (run >= prefix_k) break;
+        }
+        const uint32_t bin = uint32_t(lane * PER + b);
+        *out_limit = (bin >= uint32_t(BINS - 1)) ? kDeadKey : (uint64_t(bin + 1u) << (64 - SELECT_HIST_BITS));
+        *out_admit = (bin >= uint32_t(BINS - 1)) ? n : run;
+    }
+}
+
+// How many candidates a frame still wants and how large its first rank range is (shared by the selection kernel and the kernels that
+// prepare its first range).
+__device__ __forceinline__ uint32_t select_want(const SelectArgs &p, int frame) {
+    const uint32_t n_pre = p.existing_counts ? uint32_t(p.existing_counts[frame]) : 0u;
+    const uint32_t want = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;  // pushed, then tested: at least one
+    return min(want, uint32_t(p.kp_capacity));
+}
+__device__ __forceinline__ uint32_t select_first_range(uint32_t want_kept) { return max(uint32_t(SELECT_PREFIX_FIRST), 8u * want_kept); }
+
+
 }  // namespace
 }  // namespace fdb

@@ -15,13 +15,15 @@
 //   * fd_select_candidates runs on the root over the packed keys.
 // The same code runs with all tiles on ONE device (device ordinals may repeat), which is how the single-GPU test-suite covers it.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/fd_b200.h"
-#include "fd_common.cuh"
+#include "fd_internal.h"
+#include "fd_select_common.cuh"
 
 namespace {
 
@@ -40,6 +42,17 @@ struct Tile {
     uint32_t *stage_counts = nullptr;
     size_t stage_bytes = 0;
     bool root_reads_directly = true;
+    // the candidates of the last fd_compute_candidates (device pointers, this tile's device or the root's staging copy)
+    const uint64_t *cand_keys = nullptr;
+    const uint32_t *cand_counts = nullptr;
+    uint32_t cand_capacity = 0;
+    // first-range prefilter (this tile's device): rank histogram, the limits the root derived, the compacted first range
+    uint8_t *pre = nullptr;
+    size_t pre_bytes = 0;
+    uint32_t *hist = nullptr, *pre_counts = nullptr;
+    uint64_t *limits = nullptr, *pre_keys = nullptr;
+    uint32_t pre_capacity = 0;
+    cudaEvent_t admit_done = nullptr;
     int own_count() const { return own_hi - own_lo; }
     int buf_rows() const { return buf_hi - buf_lo; }
 };
@@ -53,11 +66,13 @@ struct GatherArgs {
     uint32_t *dst_counts;
     uint32_t dst_capacity;
     uint32_t *overflow_flag;
+    const uint8_t *only_flagged;   // optional: frames whose flag is 0 are left alone
 };
 
 // Block (f, j): packs frame f's keys of every tile back to back; the blocks of a frame split each tile's keys between them.
 __global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherArgs a) {
     const int f = blockIdx.x;
+    if (a.only_flagged != nullptr && a.only_flagged[f] == 0) return;
     uint32_t offset = 0u;
     bool overflow = false;
     uint64_t *dst = a.dst + int64_t(f) * a.dst_capacity;
@@ -77,6 +92,56 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherArgs a) {
     }
 }
 
+
+// First-range prefilter, root side: the tiles' rank histograms summed per frame, the candidates counted, and the limit of the first
+// rank range derived exactly as select_kernel derives it (same histogram, same helpers), so that the tiles can compact the keys
+// below it and only those travel.  limit 0 = the frame is not prefiltered (few candidates, a first range that is the whole frame or
+// larger than the gathered slots): it goes the full-gather way.
+struct LimitsArgs {
+    const uint32_t *hist[MAX_TILES];
+    const uint32_t *counts[MAX_TILES];
+    uint32_t capacity[MAX_TILES];
+    int n_tiles;
+    uint32_t needed, kp_capacity, pre_capacity;
+    uint32_t *hist_sum;     // n_frames x 2048
+    uint64_t *limits;       // n_frames
+    uint32_t *totals;       // n_frames
+    uint32_t *overflow_flag;
+};
+
+__global__ void __launch_bounds__(256) tiled_limits_kernel(const LimitsArgs a) {
+    constexpr int BINS = 1 << fdb::SELECT_HIST_BITS;
+    __shared__ uint32_t hist[BINS];
+    __shared__ uint64_t s_limit;
+    __shared__ uint32_t s_admit;
+    const int f = blockIdx.x;
+    for (int b = threadIdx.x; b < BINS; b += blockDim.x) {
+        uint32_t sum = 0u;
+        for (int t = 0; t < a.n_tiles; ++t) sum += a.hist[t][int64_t(f) * BINS + b];
+        hist[b] = sum;
+        a.hist_sum[int64_t(f) * BINS + b] = sum;
+    }
+    uint32_t total = 0u;
+    bool overflow = false;
+    for (int t = 0; t < a.n_tiles; ++t) {
+        const uint32_t c = a.counts[t][f];
+        overflow |= c > a.capacity[t];
+        total += min(c, a.capacity[t]);
+    }
+    if (threadIdx.x == 0) {
+        s_limit = 0ull;
+        s_admit = 0u;
+        a.totals[f] = total;
+        if (overflow) atomicExch(a.overflow_flag, 1u);
+    }
+    __syncthreads();
+    const uint32_t want = min(a.needed > 0u ? a.needed : 1u, a.kp_capacity);   // no pre-existing features on tiles
+    const uint32_t prefix_k = fdb::select_first_range(want);
+    if (total > uint32_t(fdb::SELECT_PREFIX_MIN) && prefix_k < total && threadIdx.x < 32) fdb::warp_prefix_limit(hist, prefix_k, total, &s_limit, &s_admit);
+    __syncthreads();
+    if (threadIdx.x == 0) a.limits[f] = (s_limit == fdb::kDeadKey || s_admit > a.pre_capacity) ? 0ull : s_limit;
+}
+
 }  // namespace
 
 struct fd_tiled {
@@ -90,7 +155,16 @@ struct fd_tiled {
     size_t gathered_bytes = 0, counts_bytes = 0;
     uint32_t gathered_capacity = 0;
     uint64_t halo_bytes = 0;
-    cudaEvent_t gather_done = nullptr;   // root stream: the gather kernel has read the tiles' key slots
+    cudaEvent_t gather_done = nullptr;   // root stream: the root's kernels have read the tiles' key slots and first ranges
+    cudaEvent_t limits_ready = nullptr;  // root stream: the limits have been pushed to the tiles
+    bool full_gathered = false;          // t->gathered holds every frame's keys of the last candidates
+    bool prefilter = true;               // FD_B200_TILED_PREFILTER=0: always gather every key (testing knob)
+    uint8_t *root_pre = nullptr;         // root side of the prefilter: hist_sum | limits | totals | need_more | pre_counts | pre_keys
+    size_t root_pre_bytes = 0;
+    uint32_t *hist_sum = nullptr, *totals = nullptr, *root_pre_counts = nullptr;
+    uint64_t *root_limits = nullptr, *root_pre_keys = nullptr;
+    uint8_t *need_more = nullptr;
+    uint32_t root_pre_capacity = 0;
     Tile &root() { return tiles[0]; }
 };
 
@@ -206,16 +280,29 @@ fd_status bind_tiles(fd_tiled *t) {
     return FD_OK;
 }
 
-fd_status run_candidates_and_gather(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile) {
+constexpr uint32_t PRE_CAPACITY = 65536;   // slots per frame for the gathered first rank ranges (a larger first range goes the full-gather way)
+
+fd_status grow(fd_tiled *t, int device, cudaStream_t stream, uint8_t **buf, size_t *have, size_t need) {
+    if (need <= *have) return FD_OK;
+    TD_CUDA(t, cudaSetDevice(device));
+    TD_CUDA(t, cudaStreamSynchronize(stream));
+    if (*buf) TD_CUDA(t, cudaFree(*buf));
+    *buf = nullptr;
+    *have = 0;
+    TD_CUDA(t, cudaMalloc(reinterpret_cast<void **>(buf), need));
+    *have = need;
+    return FD_OK;
+}
+
+// fd_compute_candidates on every tile (and, with the prefilter, each tile's rank histogram); cand_done marks the end of both.
+fd_status tile_candidates(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile, bool with_hist) {
     if (!t->have_frames) return tfail(t, FD_ERR_NOT_READY, "fd_tiled: no frames distributed");
     if (!params) return tfail(t, FD_ERR_INVALID_ARGUMENT, "params is null");
-    GatherArgs g = {};
-    g.n_frames = t->n_frames;
-    uint64_t total_capacity = 0;
     Tile &root = t->root();
+    constexpr size_t BINS = size_t(1) << fdb::SELECT_HIST_BITS;
     for (Tile &tl : t->tiles) {
         if (tl.own_count() == 0) continue;
-        // the previous gather may still be reading this tile's key slots
+        // the root's kernels of the previous call may still be reading this tile's key slots
         TD_CUDA(t, cudaSetDevice(tl.device));
         if (t->gather_done) TD_CUDA(t, cudaStreamWaitEvent(tl.stream, t->gather_done, 0));
         TD_FD(t, tl, fd_compute_candidates(tl.ctx, params, cand_capacity_per_tile));
@@ -223,6 +310,27 @@ fd_status run_candidates_and_gather(fd_tiled *t, const fd_detect_params *params,
         const uint32_t *counts = nullptr;
         uint32_t cap = 0;
         TD_FD(t, tl, fd_device_candidates(tl.ctx, &keys, &counts, &cap));
+        if (with_hist) {
+            tl.pre_capacity = std::min(cap, PRE_CAPACITY);
+            const size_t nf = size_t(t->n_frames);
+            const size_t need = nf * BINS * 4 + nf * 8 + nf * 4 + nf * tl.pre_capacity * 8 + 64;
+            fd_status st = grow(t, tl.device, tl.stream, &tl.pre, &tl.pre_bytes, need);
+            if (st != FD_OK) return st;
+            tl.pre_keys = reinterpret_cast<uint64_t *>(tl.pre);
+            tl.limits = tl.pre_keys + nf * tl.pre_capacity;
+            tl.hist = reinterpret_cast<uint32_t *>(tl.limits + nf);
+            tl.pre_counts = tl.hist + nf * BINS;
+            TD_CUDA(t, cudaSetDevice(tl.device));
+            TD_CUDA(t, cudaMemsetAsync(tl.hist, 0, nf * BINS * 4 + nf * 4, tl.stream));   // histogram and first-range counts
+            fdb::SelectArgs a = {};
+            a.n_frames = t->n_frames;
+            a.cand_keys = const_cast<uint64_t *>(keys);
+            a.cand_counts = counts;
+            a.cand_capacity = cap;
+            a.pre_hist = tl.hist;
+            a.hist_always = 1;
+            TD_CUDA(t, fdb::launch_select_hist(a, tl.stream));
+        }
         if (!tl.root_reads_directly) {
             // no peer access from the root: the whole key slots travel as copies (more bytes, same result)
             const size_t kb = size_t(t->n_frames) * cap * 8, cb = size_t(t->n_frames) * 4;
@@ -241,14 +349,16 @@ fd_status run_candidates_and_gather(fd_tiled *t, const fd_detect_params *params,
             keys = tl.stage_keys;
             counts = tl.stage_counts;
         }
+        tl.cand_keys = keys;
+        tl.cand_counts = counts;
+        tl.cand_capacity = cap;
         TD_CUDA(t, cudaSetDevice(tl.device));
         TD_CUDA(t, cudaEventRecord(tl.cand_done, tl.stream));
-        g.keys[g.n_tiles] = keys;
-        g.counts[g.n_tiles] = counts;
-        g.capacity[g.n_tiles] = cap;
-        ++g.n_tiles;
-        total_capacity += cap;
     }
+    // the root-side slots of the full gather (filled by full_gather, for all frames or for the flagged ones)
+    uint64_t total_capacity = 0;
+    for (Tile &tl : t->tiles)
+        if (tl.own_count() > 0) total_capacity += tl.cand_capacity;
     const uint32_t dst_cap = uint32_t(std::min<uint64_t>(total_capacity, uint64_t(t->rows) * t->cols));
     TD_CUDA(t, cudaSetDevice(root.device));
     const size_t need = size_t(t->n_frames) * dst_cap * 8, need_counts = size_t(t->n_frames) * 4;
@@ -268,23 +378,153 @@ fd_status run_candidates_and_gather(fd_tiled *t, const fd_detect_params *params,
     for (Tile &tl : t->tiles)
         if (tl.own_count() > 0) TD_CUDA(t, cudaStreamWaitEvent(root.stream, tl.cand_done, 0));
     TD_CUDA(t, cudaMemsetAsync(t->flag, 0, 16, root.stream));
-    g.dst = t->gathered;
-    g.dst_counts = t->gathered_counts;
-    g.dst_capacity = dst_cap;
-    g.overflow_flag = t->flag;
-    if (g.n_tiles > 0) {
-        // enough blocks per frame to keep the copy near the link / HBM rate whatever the frame count
-        const int per_frame = std::max(1, std::min(64, (148 * 8 + t->n_frames - 1) / t->n_frames));
-        gather_tiles_kernel<<<dim3(unsigned(t->n_frames), unsigned(per_frame)), 256, 0, root.stream>>>(g);
-        TD_CUDA(t, cudaGetLastError());
-        if (!t->gather_done) TD_CUDA(t, cudaEventCreateWithFlags(&t->gather_done, cudaEventDisableTiming));
-        TD_CUDA(t, cudaEventRecord(t->gather_done, root.stream));
-    } else {
-        TD_CUDA(t, cudaMemsetAsync(t->gathered_counts, 0, need_counts, root.stream));
-    }
     t->have_candidates = true;
     t->have_keypoints = false;
+    t->full_gathered = false;
     return FD_OK;
+}
+
+GatherArgs gather_args(fd_tiled *t, bool first_ranges) {
+    GatherArgs g = {};
+    g.n_frames = t->n_frames;
+    for (Tile &tl : t->tiles) {
+        if (tl.own_count() == 0) continue;
+        g.keys[g.n_tiles] = first_ranges ? tl.pre_keys : tl.cand_keys;
+        g.counts[g.n_tiles] = first_ranges ? tl.pre_counts : tl.cand_counts;
+        g.capacity[g.n_tiles] = first_ranges ? tl.pre_capacity : tl.cand_capacity;
+        ++g.n_tiles;
+    }
+    g.overflow_flag = t->flag;
+    return g;
+}
+
+fd_status launch_gather(fd_tiled *t, const GatherArgs &g) {
+    Tile &root = t->root();
+    TD_CUDA(t, cudaSetDevice(root.device));
+    // enough blocks per frame to keep the copy near the link / HBM rate whatever the frame count
+    const int per_frame = std::max(1, std::min(64, (148 * 8 + t->n_frames - 1) / t->n_frames));
+    gather_tiles_kernel<<<dim3(unsigned(t->n_frames), unsigned(per_frame)), 256, 0, root.stream>>>(g);
+    TD_CUDA(t, cudaGetLastError());
+    return FD_OK;
+}
+
+fd_status mark_tiles_read(fd_tiled *t) {   // from here on the tiles may overwrite their key slots / first ranges
+    Tile &root = t->root();
+    TD_CUDA(t, cudaSetDevice(root.device));
+    if (!t->gather_done) TD_CUDA(t, cudaEventCreateWithFlags(&t->gather_done, cudaEventDisableTiming));
+    TD_CUDA(t, cudaEventRecord(t->gather_done, root.stream));
+    return FD_OK;
+}
+
+// Every key of every tile (of the frames whose flag is set, if flags are given), packed per frame on the root.
+fd_status full_gather(fd_tiled *t, const uint8_t *only_flagged) {
+    GatherArgs g = gather_args(t, false);
+    g.dst = t->gathered;
+    g.dst_counts = t->gathered_counts;
+    g.dst_capacity = t->gathered_capacity;
+    g.only_flagged = only_flagged;
+    if (g.n_tiles > 0) {
+        fd_status st = launch_gather(t, g);
+        if (st != FD_OK) return st;
+    } else {
+        TD_CUDA(t, cudaMemsetAsync(t->gathered_counts, 0, size_t(t->n_frames) * 4, t->root().stream));
+    }
+    if (only_flagged == nullptr) t->full_gathered = true;
+    return FD_OK;
+}
+
+// Selection with the first-range prefilter: only the keys below each frame's first rank limit travel to the root; a frame that
+// needs more than its first range (or is too small to have one) is flagged on the device and goes the full-gather way afterwards --
+// both launches are enqueued unconditionally and skip the frames that are not theirs, so nothing waits for the host.
+fd_status prefiltered_select(fd_tiled *t, const fd_detect_params *params) {
+    Tile &root = t->root();
+    constexpr size_t BINS = size_t(1) << fdb::SELECT_HIST_BITS;
+    const size_t nf = size_t(t->n_frames);
+    t->root_pre_capacity = uint32_t(std::min<uint64_t>(PRE_CAPACITY, t->gathered_capacity));
+    const size_t need = nf * t->root_pre_capacity * 8 + nf * 8 + nf * BINS * 4 + nf * 4 + nf * 4 + nf + 64;
+    fd_status st = grow(t, root.device, root.stream, &t->root_pre, &t->root_pre_bytes, need);
+    if (st != FD_OK) return st;
+    t->root_pre_keys = reinterpret_cast<uint64_t *>(t->root_pre);
+    t->root_limits = t->root_pre_keys + nf * t->root_pre_capacity;
+    t->hist_sum = reinterpret_cast<uint32_t *>(t->root_limits + nf);
+    t->totals = t->hist_sum + nf * BINS;
+    t->root_pre_counts = t->totals + nf;
+    t->need_more = reinterpret_cast<uint8_t *>(t->root_pre_counts + nf);
+
+    // limits from the summed histograms (the root stream already waits for every tile's candidates and histogram)
+    TD_CUDA(t, cudaSetDevice(root.device));
+    LimitsArgs la = {};
+    for (Tile &tl : t->tiles) {
+        if (tl.own_count() == 0) continue;
+        la.hist[la.n_tiles] = tl.hist;
+        la.counts[la.n_tiles] = tl.cand_counts;
+        la.capacity[la.n_tiles] = tl.cand_capacity;
+        ++la.n_tiles;
+    }
+    la.needed = params->needed_feature_num;
+    la.kp_capacity = std::max<uint32_t>(1u, std::min<uint32_t>(params->needed_feature_num, 1u << 20));   // as run_select sizes the keypoint slots
+    la.pre_capacity = t->root_pre_capacity;
+    la.hist_sum = t->hist_sum;
+    la.limits = t->root_limits;
+    la.totals = t->totals;
+    la.overflow_flag = t->flag;
+    tiled_limits_kernel<<<unsigned(t->n_frames), 256, 0, root.stream>>>(la);
+    TD_CUDA(t, cudaGetLastError());
+    for (Tile &tl : t->tiles)
+        if (tl.own_count() > 0) TD_CUDA(t, cudaMemcpyPeerAsync(tl.limits, tl.device, t->root_limits, root.device, nf * 8, root.stream));
+    if (!t->limits_ready) TD_CUDA(t, cudaEventCreateWithFlags(&t->limits_ready, cudaEventDisableTiming));
+    TD_CUDA(t, cudaEventRecord(t->limits_ready, root.stream));
+
+    // the tiles compact their keys below the limits
+    for (Tile &tl : t->tiles) {
+        if (tl.own_count() == 0) continue;
+        TD_CUDA(t, cudaSetDevice(tl.device));
+        TD_CUDA(t, cudaStreamWaitEvent(tl.stream, t->limits_ready, 0));
+        fdb::SelectArgs a = {};
+        a.n_frames = t->n_frames;
+        a.cand_keys = const_cast<uint64_t *>(tl.cand_keys);
+        a.cand_counts = tl.cand_counts;
+        a.cand_capacity = tl.cand_capacity;
+        a.ext_limits = tl.limits;
+        a.pre_keys = tl.pre_keys;
+        a.pre_counts = tl.pre_counts;
+        a.pre_capacity = tl.pre_capacity;
+        TD_CUDA(t, fdb::launch_select_admit(a, tl.stream));
+        if (!tl.admit_done) TD_CUDA(t, cudaEventCreateWithFlags(&tl.admit_done, cudaEventDisableTiming));
+        TD_CUDA(t, cudaEventRecord(tl.admit_done, tl.stream));
+    }
+
+    // the root gathers the first ranges, selects on them, and deals with the frames that needed more
+    TD_CUDA(t, cudaSetDevice(root.device));
+    for (Tile &tl : t->tiles)
+        if (tl.own_count() > 0) TD_CUDA(t, cudaStreamWaitEvent(root.stream, tl.admit_done, 0));
+    TD_CUDA(t, cudaMemsetAsync(t->need_more, 0, nf, root.stream));
+    GatherArgs g = gather_args(t, true);
+    g.dst = t->root_pre_keys;
+    g.dst_counts = t->root_pre_counts;
+    g.dst_capacity = t->root_pre_capacity;
+    st = launch_gather(t, g);
+    if (st != FD_OK) return st;
+    fd_select_prefilter pf = {};
+    pf.total_counts = t->totals;
+    pf.total_capacity = t->gathered_capacity;
+    pf.hist = t->hist_sum;
+    pf.pre_keys = t->root_pre_keys;
+    pf.pre_counts = t->root_pre_counts;
+    pf.pre_capacity = t->root_pre_capacity;
+    pf.need_more = t->need_more;
+    TD_FD(t, root, fd_internal_select_first_range(root.ctx, params, &pf, t->rows, t->cols, t->n_frames));
+    st = full_gather(t, t->need_more);
+    if (st != FD_OK) return st;
+    TD_FD(t, root, fd_internal_select_flagged(root.ctx, params, t->gathered, t->totals, t->gathered_capacity, t->need_more, t->rows, t->cols, t->n_frames));
+    return mark_tiles_read(t);
+}
+
+fd_status ensure_full_gather(fd_tiled *t) {   // the prefiltered detection gathers first ranges only: the callers that read every key pay for the rest
+    if (t->full_gathered) return FD_OK;
+    fd_status st = full_gather(t, nullptr);
+    if (st != FD_OK) return st;
+    return mark_tiles_read(t);
 }
 
 fd_status check_flag(fd_tiled *t) {
@@ -312,6 +552,7 @@ fd_status fd_tiled_create(const int *device_ordinals, int n_tiles, fd_tiled **ou
     fd_tiled *t = new (std::nothrow) fd_tiled();
     if (!t) return FD_ERR_OUT_OF_MEMORY;
     t->tiles.resize(size_t(n_tiles));
+    if (const char *env = std::getenv("FD_B200_TILED_PREFILTER")) t->prefilter = (env[0] != '0');
     for (int k = 0; k < n_tiles; ++k) {
         Tile &tl = t->tiles[k];
         tl.device = device_ordinals[k];
@@ -362,10 +603,14 @@ fd_status fd_tiled_destroy(fd_tiled *t) {
         if (t->gather_done) cudaEventDestroy(t->gather_done);
         for (Tile &tl : t->tiles)
             if (tl.stage_keys) cudaFree(tl.stage_keys);
+        if (t->root_pre) cudaFree(t->root_pre);
+        if (t->limits_ready) cudaEventDestroy(t->limits_ready);
     }
     for (Tile &tl : t->tiles) {
         cudaSetDevice(tl.device);
         if (tl.buf) cudaFree(tl.buf);
+        if (tl.pre) cudaFree(tl.pre);
+        if (tl.admit_done) cudaEventDestroy(tl.admit_done);
         if (tl.own_ready) cudaEventDestroy(tl.own_ready);
         if (tl.halo_done) cudaEventDestroy(tl.halo_done);
         if (tl.cand_done) cudaEventDestroy(tl.cand_done);
@@ -460,15 +705,30 @@ uint64_t fd_tiled_halo_bytes(const fd_tiled *t) { return t ? t->halo_bytes : 0; 
 
 fd_status fd_tiled_compute_candidates(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile) {
     if (!t) return FD_ERR_INVALID_ARGUMENT;
-    return run_candidates_and_gather(t, params, cand_capacity_per_tile);
+    fd_status st = tile_candidates(t, params, cand_capacity_per_tile, false);
+    if (st != FD_OK) return st;
+    st = full_gather(t, nullptr);
+    if (st != FD_OK) return st;
+    return mark_tiles_read(t);
 }
 
 fd_status fd_tiled_detect(fd_tiled *t, const fd_detect_params *params, int cand_capacity_per_tile) {
     if (!t) return FD_ERR_INVALID_ARGUMENT;
-    fd_status st = run_candidates_and_gather(t, params, cand_capacity_per_tile);
+    bool prefilter = t->prefilter;
+    for (const Tile &tl : t->tiles) prefilter = prefilter && (tl.own_count() == 0 || tl.root_reads_directly);
+    fd_status st = tile_candidates(t, params, cand_capacity_per_tile, prefilter);
     if (st != FD_OK) return st;
     Tile &root = t->root();
-    TD_FD(t, root, fd_select_candidates(root.ctx, params, t->gathered, t->gathered_counts, t->gathered_capacity, t->rows, t->cols, t->n_frames));
+    if (prefilter) {
+        st = prefiltered_select(t, params);
+        if (st != FD_OK) return st;
+    } else {
+        st = full_gather(t, nullptr);
+        if (st != FD_OK) return st;
+        st = mark_tiles_read(t);
+        if (st != FD_OK) return st;
+        TD_FD(t, root, fd_select_candidates(root.ctx, params, t->gathered, t->gathered_counts, t->gathered_capacity, t->rows, t->cols, t->n_frames));
+    }
     t->have_keypoints = true;
     return FD_OK;
 }
@@ -486,6 +746,10 @@ fd_status fd_tiled_sync(fd_tiled *t) {
 fd_status fd_tiled_candidate_counts(fd_tiled *t, int32_t *host_counts) {
     if (!t || !host_counts) return FD_ERR_INVALID_ARGUMENT;
     if (!t->have_candidates) return tfail(t, FD_ERR_NOT_READY, "fd_tiled: no candidates computed");
+    {
+        const fd_status st_g = ensure_full_gather(t);
+        if (st_g != FD_OK) return st_g;
+    }
     fd_status st = check_flag(t);
     if (st != FD_OK) return st;
     Tile &root = t->root();
@@ -497,6 +761,10 @@ fd_status fd_tiled_candidate_counts(fd_tiled *t, int32_t *host_counts) {
 fd_status fd_tiled_device_candidates(fd_tiled *t, const uint64_t **dev_keys, const uint32_t **dev_counts, uint32_t *capacity, int *device) {
     if (!t) return FD_ERR_INVALID_ARGUMENT;
     if (!t->have_candidates) return tfail(t, FD_ERR_NOT_READY, "fd_tiled: no candidates computed");
+    {
+        const fd_status st_g = ensure_full_gather(t);
+        if (st_g != FD_OK) return st_g;
+    }
     if (dev_keys) *dev_keys = t->gathered;
     if (dev_counts) *dev_counts = t->gathered_counts;
     if (capacity) *capacity = t->gathered_capacity;
@@ -507,6 +775,10 @@ fd_status fd_tiled_device_candidates(fd_tiled *t, const uint64_t **dev_keys, con
 fd_status fd_tiled_download_candidates(fd_tiled *t, int frame, fd_candidate *host_cand, int64_t capacity, int64_t *n_out) {
     if (!t || !n_out) return FD_ERR_INVALID_ARGUMENT;
     if (!t->have_candidates) return tfail(t, FD_ERR_NOT_READY, "fd_tiled: no candidates computed");
+    {
+        const fd_status st_g = ensure_full_gather(t);
+        if (st_g != FD_OK) return st_g;
+    }
     if (frame < 0 || frame >= t->n_frames) return tfail(t, FD_ERR_INVALID_ARGUMENT, "frame out of range");
     fd_status st = check_flag(t);
     if (st != FD_OK) return st;

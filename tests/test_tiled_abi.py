@@ -125,3 +125,34 @@ def test_config3_frame_tiled_over_all_gpus():
         kp, cnt = td.keypoints(200)
         assert cnt[0] == cnt_ref[0] == 200 and np.array_equal(kp[0, :200], kp_ref[0, :200])
         assert np.array_equal(td.candidates(0), cand_ref[0])
+
+
+def test_first_range_prefilter_equals_full_gather(monkeypatch):
+    """fd_tiled_detect ships only the keys below each frame's first rank limit to the root (tile histograms summed there, limits handed
+    back, frames that need more flagged on the device and finished from a full gather); FD_B200_TILED_PREFILTER=0 gathers every key as
+    before.  Same keypoints and candidates either way: frames with many candidates (the prefiltered way), with few (flagged), FAST at the
+    reference's default threshold (a first range larger than the gathered slots), needed counts that one range cannot satisfy."""
+    frames = np.stack([synth(752, 480, 60 + i) for i in range(3)])
+    cases = [(fd.HARRIS, 30.0, 20, 200, 12), (fd.HARRIS, 0.1, 3, 4000, 12), (fd.FAST, 0.1, 15, 200, 12), (fd.FAST, 10.0, 20, 200, 9),
+             (fd.SHI_TOMAS, 40.0, 20, 1000, 12), (fd.HARRIS, 30.0, 20, 0, 12), (fd.HARRIS, 1e9, 20, 50, 12)]
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("FD_B200_TILED_PREFILTER", flag)
+        with fd.TiledDetector(_devices(3)) as td:
+            td.upload(frames)
+            res = []
+            for kind, thr, d, n, fast_n in cases:
+                prm = fd.DetectParams(kind, thr, d, n, fast_n=fast_n)
+                td.detect(prm)
+                kp, cnt = td.keypoints(max(n, 1))
+                res.append((kp.copy(), cnt.copy(), td.candidate_counts(), [td.candidates(f) for f in range(len(frames))]))
+                td.detect(prm)                                     # and again on warm buffers
+                kp2, cnt2 = td.keypoints(max(n, 1))
+                assert np.array_equal(cnt, cnt2) and np.array_equal(kp, kp2)
+            outs.append(res)
+    for (kp0, cnt0, cc0, cand0), (kp1, cnt1, cc1, cand1), case in zip(outs[0], outs[1], cases):
+        assert np.array_equal(cnt0, cnt1) and np.array_equal(cc0, cc1), case
+        for f in range(len(frames)):
+            assert np.array_equal(kp0[f, :cnt0[f]], kp1[f, :cnt1[f]]) and np.array_equal(cand0[f], cand1[f]), (case, f)
+    kp_ref, cnt_ref, _ = _untiled(frames, fd.DetectParams(fd.HARRIS, 30.0, 20, 200), 200)
+    assert np.array_equal(outs[1][0][1], cnt_ref) and all(np.array_equal(outs[1][0][0][f, :cnt_ref[f]], kp_ref[f, :cnt_ref[f]]) for f in range(3))
