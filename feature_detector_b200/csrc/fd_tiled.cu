@@ -10,9 +10,15 @@
 //     ordered by events -- 2 x 3 x cols bytes per interior seam and frame;
 //   * fd_compute_candidates runs per tile (fd_set_tile: candidates for the own rows, absolute row numbers, FAST's running offset
 //     indexed by the absolute pixel position, so tiles are seam-free);
-//   * one gather kernel on the root device reads the tiles' key slots and counts through peer pointers (plain loads over NVLink)
-//     and packs each frame's keys back to back -- counts never visit the host;
-//   * fd_select_candidates runs on the root over the packed keys.
+//   * the selection needs the best-ranked few thousand of a frame's 10^5 - 10^6 candidates, so only those travel: every tile builds the
+//     rank histogram of its keys (select_hist_kernel), the root sums the histograms through peer pointers, derives each frame's first
+//     rank limit exactly as the selection kernel would (tiled_limits_kernel) and hands the limits back (one small peer copy per tile);
+//     the tiles compact the keys below them (select_admit_kernel), one gather kernel on the root packs those first ranges (plain loads
+//     over NVLink, counts included -- no count ever visits the host), and the selection runs on them;
+//   * a frame that needs more than its first range (or is too small to have one) is flagged on the device; a conditional full gather
+//     and a second selection launch -- both enqueued unconditionally, both skipping the frames that are not theirs -- finish it, so
+//     the result is exact whatever the data and still nothing waits for the host (FD_B200_TILED_PREFILTER=0: always gather every key);
+//   * fd_tiled_compute_candidates (the candidate list itself is the result) gathers every key.
 // The same code runs with all tiles on ONE device (device ordinals may repeat), which is how the single-GPU test-suite covers it.
 #include <algorithm>
 #include <cstdlib>

@@ -175,9 +175,11 @@ fd_status fd_select_candidates(fd_context *ctx, const fd_detect_params *params, 
  * 3-row halo.  Own rows come from the host (fd_tiled_upload_frames: each device receives only its own rows) or from frames resident
  * on one device (fd_tiled_scatter_device_frames: peer copies); the halo rows then travel tile to tile as device-to-device peer copies
  * (NVLink when peer access is available), 2 x 3 x cols bytes per interior seam and frame, ordered by events.  fd_tiled_detect runs
- * fd_compute_candidates per tile, packs the tiles' candidate keys on the first tile's device with a kernel that reads the other
- * devices' key slots and counts through peer pointers (no count ever visits the host), and selects there.  Nothing synchronises with
- * the host until a download / fd_tiled_sync.  Pre-existing features are not supported on tiles.  Results equal the untiled run
+ * fd_compute_candidates per tile and selects on the first tile's device; only the best-ranked few thousand keys of a frame travel
+ * there (tile rank histograms summed on that device, the first rank limit handed back, the keys below it compacted per tile and read
+ * through peer pointers -- no count ever visits the host), and a frame that needs more is finished from a full gather of its keys, so
+ * the result is exactly the untiled one.  fd_tiled_compute_candidates packs EVERY key of every tile on the first tile's device (the
+ * candidate list as a result).  Nothing synchronises with the host until a download / fd_tiled_sync.  Pre-existing features are not supported on tiles.  Results equal the untiled run
  * (tests/test_tiled_abi.py). */
 typedef struct fd_tiled fd_tiled;
 fd_status fd_tiled_create(const int *device_ordinals, int n_tiles, fd_tiled **out);   /* n_tiles <= 16 */
