@@ -661,9 +661,11 @@ def main():
                     c3["row_tiled"] = {"tiles": len(tiles), "devices": sorted(set(tiles)), "ms_per_step_detect": round(s_t * 1e3, 4), "ms_per_step_candidates_and_gather": round(s_c * 1e3, 4),
                                        "untiled_one_gpu_ms_per_step": c3["ms_per_step"], "halo_bytes_per_step": td.halo_bytes,
                                        "equals_untiled": same_t, "mpixel_s": round(64 * 3840 * 2160 / s_t / 1e6, 1),
-                                       "what": "per step: halo exchange (device-to-device peer copies of 3 rows per seam side and frame) -> fd_compute_candidates per tile -> "
-                                               "peer-read key gather on device 0 -> one fd_select_candidates; frames' own rows resident on their GPUs; host clock around "
-                                               f"{reps} steps with a sync of every tile stream on both sides"}
+                                       "what": "per step (fd_tiled_exchange_halos + fd_tiled_detect): halo exchange (device-to-device peer copies of 3 rows per seam side and frame) -> "
+                                               "fd_compute_candidates + rank histogram per tile -> first rank limits on device 0 -> first ranges compacted per tile and "
+                                               "gathered on device 0 by peer reads -> one global selection (frames that need more are finished from a conditional full "
+                                               "gather); ms_per_step_candidates_and_gather = fd_tiled_compute_candidates, which gathers every key; frames' own rows resident "
+                                               f"on their GPUs; host clock around {reps} steps with a sync of every tile stream on both sides"}
                     ok &= same_t
             except Exception as e:   # reported and fatal for the parity flag only if it was a mismatch
                 c3["row_tiled"] = {"error": repr(e)[:400]}
