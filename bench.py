@@ -543,6 +543,16 @@ def main():
         extras["single frame, host to host, one call (fd_detect_describe_host: one synchronisation)"] = {
             "latency_us_median": round(float(np.median(lat)) * 1e6, 1), "latency_us_p90": round(float(np.percentile(lat, 90)) * 1e6, 1),
             "mpixel_s": round(px / float(np.median(lat)) / 1e6, 1)}
+        with fd.Context(local_rank) as own:      # the drop-in classes' situation: an object with its own context and stream
+            lat = []
+            for i in range(220):
+                t0 = time.perf_counter()
+                own.detect_describe_host(one, det, brief, NEEDED, CAND_CAPACITY)
+                if i >= 20:
+                    lat.append(time.perf_counter() - t0)
+        extras["single frame, host to host, one call, on a context of its own"] = {
+            "latency_us_median": round(float(np.median(lat)) * 1e6, 1), "latency_us_p90": round(float(np.percentile(lat, 90)) * 1e6, 1),
+            "mpixel_s": round(px / float(np.median(lat)) / 1e6, 1)}
         ctx.bind_device(d_frames.data_ptr(), H, W, n)
 
         # ---- dense-map output modes (reported separately; 1 B/px in + the map out) ----

@@ -82,10 +82,12 @@ struct fd_context {
     int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
+    int select_list = -1;           // FD_B200_SELECT_LIST: tuning knob, entries of selection's shared-memory live lists (-1: sized from what the SM has left)
     bool select_prepare = true;     // FD_B200_SELECT_PREPARE=0: testing knob, selection always builds its rank histogram and first range itself
 
     void *host_stage = nullptr;     // pinned staging block of fd_detect_describe_host
     size_t host_stage_bytes = 0;
+    DevBuf result_pack;             // device image of that block when the results are small enough to leave in one copy
     DevBuf nn_desc, nn_user_desc, desc_float, lsd_work, float_slot[2], matches;
     int match_pairs = 0, match_capacity = 0;
     bool have_desc_float = false;
@@ -328,17 +330,22 @@ void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_fr
     const int64_t base_items = int64_t(n_frames) * n_strips;
     int64_t want_bands = (ctx->items_per_warp * total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
     int64_t max_bands = std::max(1, interior_rows / min_band);
-    // A few frames (the drop-in classes' one frame per call) cannot fill the grid with bands that tall: what counts there is the
-    // latency of the longest band, not the halo rows shorter bands read twice.
-    if (base_items * max_bands < total_warps) max_bands = std::max(1, interior_rows / std::max(8, min_band / 4));
+    // A few frames (the drop-in classes' one frame per call) cannot fill the grid with bands that tall.  What counts there is the
+    // latency of one band on one warp -- a warp alone on its scheduler retires an instruction every few cycles -- not the halo rows
+    // shorter bands read twice: one item per warp, bands down to four rows.
+    if (base_items * max_bands < total_warps) {
+        max_bands = std::max(1, interior_rows / 4);
+        want_bands = (total_warps + base_items - 1) / std::max<int64_t>(base_items, 1);
+    }
     want_bands = std::max<int64_t>(1, std::min<int64_t>(want_bands, max_bands));
     band_rows = int((interior_rows + want_bands - 1) / want_bands);
     band_rows = std::max(band_rows, 1);
     band_rows = (band_rows + band_multiple - 1) / band_multiple * band_multiple;  // kernels that unroll their row loop
     n_bands = (interior_rows + band_rows - 1) / band_rows;
     n_items = base_items * n_bands;
-    const int64_t ctas_needed = (n_items + warps_per_cta - 1) / warps_per_cta;
-    grid = int(std::max<int64_t>(1, std::min<int64_t>(grid, ctas_needed)));
+    // Warps take items from a shared counter, so fewer items than warps still spread over the SMs when every SM gets a CTA: one
+    // frame's few hundred items finish in the time of one item, not of a CTA's worth of them on a handful of SMs.
+    grid = int(std::max<int64_t>(1, std::min<int64_t>(grid, n_items)));
 }
 
 fd_status require_frames(fd_context *ctx) {
@@ -543,6 +550,8 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
         a.cell_stride = int64_t(cell_bytes);
     }
+    a.smem_list_offset = uint32_t(cell_bytes);
+    a.smem_list = ctx->select_list >= 0 ? (a.cells_in_smem ? uint32_t(ctx->select_list) & ~31u : 0u) : select_smem_list(a);
     a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
     FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 16));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
@@ -618,6 +627,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
     if (const char *env = std::getenv("FD_B200_SELECT_PREPARE")) ctx->select_prepare = (env[0] != '0');
+    if (const char *env = std::getenv("FD_B200_SELECT_LIST")) ctx->select_list = std::max(0, std::min(8192, std::atoi(env)));
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -631,7 +641,7 @@ fd_status fd_destroy(fd_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->owned_frames, &ctx->lut, &ctx->segs, &ctx->keys, &ctx->keys_scratch, &ctx->counts, &ctx->flags, &ctx->cells, &ctx->alive, &ctx->kept, &ctx->pre_hist, &ctx->pre_keys, &ctx->kp,
                       &ctx->kp_counts, &ctx->user_kp, &ctx->user_counts, &ctx->desc, &ctx->mask_bits, &ctx->mask_rowbase, &ctx->mask_prefix,
-                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1], &ctx->matches})
+                      &ctx->existing_xy, &ctx->existing_counts, &ctx->lsd_norm, &ctx->lsd_angle, &ctx->lsd_keys, &ctx->lsd_counts, &ctx->lsd_sorted, &ctx->lsd_hist, &ctx->lsd_start, &ctx->lsd_bucketed, &ctx->lsd_item_counts, &ctx->lsd_chunk_sum, &ctx->nn_desc, &ctx->nn_user_desc, &ctx->desc_float, &ctx->lsd_work, &ctx->float_slot[0], &ctx->float_slot[1], &ctx->matches, &ctx->result_pack})
         release(*b);
     if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -985,6 +995,42 @@ fd_status fd_describe_selected(fd_context *ctx, const fd_brief_params *params) {
     return run_brief(ctx, params, static_cast<const float4 *>(ctx->kp.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), ctx->kp_capacity);
 }
 
+}  // extern "C"
+
+namespace {
+// Results of a small call laid out on the device exactly as the pinned staging block wants them, so that they leave in ONE
+// copy instead of four (flag, counts, keypoints, descriptors): what a single-frame caller waits for is copy latency.
+// 16-byte units: [flag | counts, padded | n_frames x w keypoints | n_frames x w descriptors].
+__global__ void pack_results_kernel(const uint32_t *__restrict__ flag, const int32_t *__restrict__ counts, const uint4 *__restrict__ kp, int kp_stride,
+                                    const uint4 *__restrict__ desc, int desc_stride, int w, int n_frames, int count_units, uint4 *__restrict__ out) {
+    const int per_kp = n_frames * w;
+    const int total = 1 + count_units + per_kp + (desc != nullptr ? 2 * per_kp : 0);
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (u == 0) {
+            v.x = *flag;
+        } else if (u < 1 + count_units) {
+            const int i = (u - 1) * 4;
+            v.x = i < n_frames ? uint32_t(counts[i]) : 0u;
+            v.y = i + 1 < n_frames ? uint32_t(counts[i + 1]) : 0u;
+            v.z = i + 2 < n_frames ? uint32_t(counts[i + 2]) : 0u;
+            v.w = i + 3 < n_frames ? uint32_t(counts[i + 3]) : 0u;
+        } else if (u < 1 + count_units + per_kp) {
+            const int k = u - 1 - count_units;
+            v = kp[size_t(k / w) * kp_stride + k % w];
+        } else {
+            const int k = u - 1 - count_units - per_kp;       // two units per descriptor
+            const int slot = k >> 1;
+            v = desc[(size_t(slot / w) * desc_stride + slot % w) * 2 + (k & 1)];
+        }
+        out[u] = v;
+    }
+}
+constexpr size_t PACK_RESULTS_MAX = size_t(1) << 20;   // above this the strided copies are bandwidth-, not latency-bound
+}  // namespace
+
+extern "C" {
+
 fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, int rows, int cols, int n_frames, const fd_detect_params *det,
                                   const fd_brief_params *brief, int cand_capacity, fd_keypoint *host_kp, int32_t *host_counts, uint8_t *host_desc,
                                   int kp_capacity) {
@@ -1001,7 +1047,8 @@ fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, i
     }
     // every result comes back through one pinned staging block and ONE synchronisation
     const int w = std::min(kp_capacity, ctx->kp_capacity);
-    const size_t kp_bytes = size_t(n_frames) * w * sizeof(float4), cnt_bytes = size_t(n_frames) * 4, desc_bytes = brief ? size_t(n_frames) * w * 32 : 0;
+    const int count_units = (n_frames + 3) / 4;
+    const size_t kp_bytes = size_t(n_frames) * w * sizeof(float4), cnt_bytes = size_t(count_units) * 16, desc_bytes = brief ? size_t(n_frames) * w * 32 : 0;
     const size_t need = 16 + kp_bytes + cnt_bytes + desc_bytes;
     if (need > ctx->host_stage_bytes) {
         if (ctx->host_stage) FD_CUDA(ctx, cudaFreeHost(ctx->host_stage));
@@ -1011,18 +1058,30 @@ fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, i
         ctx->host_stage_bytes = need;
     }
     uint8_t *st = static_cast<uint8_t *>(ctx->host_stage);
-    FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(ctx, cudaMemcpyAsync(st + 16, ctx->kp_counts.ptr, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes, size_t(w) * sizeof(float4), ctx->kp.ptr, size_t(ctx->kp_capacity) * sizeof(float4), size_t(w) * sizeof(float4),
-                                   size_t(n_frames), cudaMemcpyDeviceToHost, ctx->stream));
-    if (brief != nullptr)
-        FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes + kp_bytes, size_t(w) * 32, ctx->desc.ptr, size_t(ctx->desc_capacity) * 32, size_t(w) * 32, size_t(n_frames),
-                                       cudaMemcpyDeviceToHost, ctx->stream));
+    if (need <= PACK_RESULTS_MAX && w > 0) {
+        FD_TRY(reserve(ctx, ctx->result_pack, need));
+        const int units = int(need / 16);
+        pack_results_kernel<<<std::min((units + 255) / 256, 592), 256, 0, ctx->stream>>>(
+            static_cast<const uint32_t *>(ctx->flags.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), static_cast<const uint4 *>(ctx->kp.ptr), ctx->kp_capacity,
+            brief ? static_cast<const uint4 *>(ctx->desc.ptr) : nullptr, ctx->desc_capacity, w, n_frames, count_units, static_cast<uint4 *>(ctx->result_pack.ptr));
+        FD_CUDA(ctx, cudaGetLastError());
+        FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->result_pack.ptr, need, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, cudaMemcpyAsync(st + 16, ctx->kp_counts.ptr, size_t(n_frames) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (w > 0) {
+            FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes, size_t(w) * sizeof(float4), ctx->kp.ptr, size_t(ctx->kp_capacity) * sizeof(float4), size_t(w) * sizeof(float4),
+                                           size_t(n_frames), cudaMemcpyDeviceToHost, ctx->stream));
+            if (brief != nullptr)
+                FD_CUDA(ctx, cudaMemcpy2DAsync(st + 16 + cnt_bytes + kp_bytes, size_t(w) * 32, ctx->desc.ptr, size_t(ctx->desc_capacity) * 32, size_t(w) * 32, size_t(n_frames),
+                                               cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
     FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     uint32_t overflow;
     std::memcpy(&overflow, st, 4);
     if (overflow != 0) return fail(ctx, FD_ERR_CAPACITY, "a frame produced more candidates than cand_capacity; raise it and run again");
-    std::memcpy(host_counts, st + 16, cnt_bytes);
+    std::memcpy(host_counts, st + 16, size_t(n_frames) * 4);
     for (int f = 0; f < n_frames; ++f) {
         if (host_counts[f] > kp_capacity) return fail(ctx, FD_ERR_CAPACITY, "host keypoint buffer too small");
         std::memcpy(host_kp + size_t(f) * kp_capacity, st + 16 + cnt_bytes + size_t(f) * w * sizeof(float4), size_t(w) * sizeof(float4));

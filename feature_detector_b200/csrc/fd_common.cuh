@@ -66,6 +66,18 @@ __device__ __forceinline__ uint32_t ld_word(const uint8_t *p) { return __ldg(rei
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Work items of the candidate kernels (frame x band x strip, one per warp at a time).  A warp's first item is its own --
+// interleaved over the CTAs, so that even a single frame's few hundred items land on every SM and no warp starts by queueing on
+// one L2 atomic -- and the rest come from a shared counter (zeroed by the host before the launch) rather than a fixed stride:
+// an item's cost follows its content, and a fixed assignment leaves a visible tail.
+__device__ __forceinline__ int64_t next_work_item(uint32_t *counter, bool first) {
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    if (first) return int64_t(blockIdx.x) + int64_t(gridDim.x) * (threadIdx.x >> 5);
+    uint32_t next = 0u;
+    if (lane_id() == 0) next = atomicAdd(counter, 1u);
+    return int64_t(gridDim.x) * warps_per_cta + int64_t(__shfl_sync(0xffffffffu, next, 0));
+}
+
 // Bits of mask word w (columns 32w .. 32w+31) that are FAST-interior columns [3, cols-4].
 __device__ __forceinline__ uint32_t fast_interior_bits(int w, int cols) {
     const int lo = max(3 - 32 * w, 0), hi = min(cols - 4 - 32 * w, 31);

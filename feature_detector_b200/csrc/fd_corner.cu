@@ -82,11 +82,8 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
     const int row_lo = p.resp_lo, row_hi = p.resp_hi;  // rows with a defined response (bound = 2, harris.cpp:90-92)
     const int col_lo = 2, col_hi = fv.cols - 3;
 
-    // work items come from a global counter (zeroed by the host before the launch) rather than a fixed stride: no tail
-    for (;;) {
-        uint32_t next = 0u;
-        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
-        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+    for (bool first = true;; first = false) {   // next_work_item (fd_common.cuh): own first item, then the shared counter
+        const int64_t item = next_work_item(p.work_counter, first);
         if (item >= p.n_items) break;
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;

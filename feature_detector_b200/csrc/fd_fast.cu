@@ -49,11 +49,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS_PER_SM) fast_kernel(co
     const int inner_cols = fv.cols - 6;
     const int last_row = fv.rows - 1;
 
-    // work items come from a global counter (zeroed by the host before the launch) rather than a fixed stride: no tail
-    for (;;) {
-        uint32_t next = 0u;
-        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
-        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+    for (bool first = true;; first = false) {   // next_work_item (fd_common.cuh): own first item, then the shared counter
+        const int64_t item = next_work_item(p.work_counter, first);
         if (item >= p.n_items) break;
         // item -> (frame, band, strip); strips fastest so neighbouring warps share L1 lines
         const int strip = int(item % p.n_strips);

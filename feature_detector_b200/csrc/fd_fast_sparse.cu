@@ -114,12 +114,8 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
     const uint32_t hm = p.absdiff_mask;   // per byte: bits at or above the largest power of two <= diff + 1
     uint32_t slot_parity = 0u;            // bit s: parity of the phase ring slot s completes next
 
-    // Work items are handed out by a global counter (zeroed by the host before the launch), not by a fixed stride: an item's cost
-    // follows its survivor count, and with ~14 items per warp a fixed assignment leaves a visible tail.
-    for (;;) {
-        uint32_t next = 0u;
-        if (lane == 0) next = atomicAdd(p.work_counter, 1u);
-        const int64_t item = int64_t(__shfl_sync(0xffffffffu, next, 0));
+    for (bool first = true;; first = false) {   // next_work_item (fd_common.cuh): own first item, then the shared counter
+        const int64_t item = next_work_item(p.work_counter, first);
         if (item >= p.n_items) break;
         const int strip = int(item % p.n_strips);
         const int64_t t = item / p.n_strips;
