@@ -82,7 +82,6 @@ struct fd_context {
     int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
-    int select_list = -1;           // FD_B200_SELECT_LIST: tuning knob, entries of selection's shared-memory live lists (-1: sized from what the SM has left)
     bool select_prepare = true;     // FD_B200_SELECT_PREPARE=0: testing knob, selection always builds its rank histogram and first range itself
 
     void *host_stage = nullptr;     // pinned staging block of fd_detect_describe_host
@@ -550,8 +549,6 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
         a.cell_stride = int64_t(cell_bytes);
     }
-    a.smem_list_offset = uint32_t(cell_bytes);
-    a.smem_list = ctx->select_list >= 0 ? (a.cells_in_smem ? uint32_t(ctx->select_list) & ~31u : 0u) : select_smem_list(a);
     a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
     FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 16));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
@@ -627,7 +624,6 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
     if (const char *env = std::getenv("FD_B200_SELECT_PREPARE")) ctx->select_prepare = (env[0] != '0');
-    if (const char *env = std::getenv("FD_B200_SELECT_LIST")) ctx->select_list = std::max(0, std::min(8192, std::atoi(env)));
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

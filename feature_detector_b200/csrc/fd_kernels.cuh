@@ -135,8 +135,6 @@ struct SelectArgs {
     int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
     uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
-    uint32_t smem_list;             // entries of each of the two shared-memory live lists behind the cell state (select_smem_list(); 0: none) ...
-    uint32_t smem_list_offset;      // ... and where they start in dynamic shared memory (select_cell_bytes())
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
     uint32_t *pre_hist;             // optional (few frames, many candidates): n_frames * 2048 rank-histogram bins, zero on entry ...
@@ -152,7 +150,6 @@ struct SelectArgs {
     uint32_t xy_xor;                // 0, or 0xFFFFFFFF when the keys carry the complemented position (NN heat maps: among equal responses the later pixel first)
 };
 size_t select_cell_bytes(int cells_x, int cells_y);
-uint32_t select_smem_list(const SelectArgs &args);
 cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream);
 // The two preparation kernels on their own (fd_tiled.cu runs them on the tiles' devices): grid = chunks x n_frames.
 cudaError_t launch_select_hist(const SelectArgs &args, cudaStream_t stream);

@@ -147,10 +147,6 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     uint32_t *cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     uint32_t *cstart = cells + n_cells;                                 // n_cells + 1 entries
     uint16_t *knew = reinterpret_cast<uint16_t *>(cstart + n_cells + 1);
-    // the per-candidate form needs neither cstart nor knew: their storage (8 bytes per cell, select_cell_bytes) is its second array of minima
-    unsigned long long *cmin2 = reinterpret_cast<unsigned long long *>(cells + n_cells + (n_cells & 1));
-    // two lists of live candidates in shared memory behind the cell state (p.smem_list entries each; 0: none)
-    uint64_t *slist = reinterpret_cast<uint64_t *>(smem + p.smem_list_offset);
     __shared__ uint32_t s_kept, s_count, s_count2[2], s_admit, s_work, s_active, s_warp[32];
     __shared__ uint64_t s_limit;
     // s_sort doubles as the 2048-bin (8 KiB) histogram of the rank-prefix search below
@@ -185,8 +181,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
         cells[i] = kEmptyCell;
         cmin[i] = kDeadKey;
-        if constexpr (BY_CELLS) knew[i] = 0;
-        else cmin2[i] = kDeadKey;
+        knew[i] = 0;
     }
     if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
@@ -436,17 +431,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                 // (1) every live candidate that a point kept in the previous round covers dies (a kept point covers itself);
                 //     the others post their key to their cell (64-bit atomicMin) and move to the next round's list;
                 // (2) a candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells is kept.
-                // The minima live in two arrays used in turn: while a round reads one, the other (last round's) is wiped, so a round
-                // costs two barriers.  A live list that fits p.smem_list entries stays in shared memory: the rounds are latency-
-                // bound (a frame per CTA), and a list in global memory costs two L2 round trips per round.
                 uint64_t *list_a = binned, *list_b = admitted_keys;
-                unsigned long long *cm = cmin, *cm_old = cmin2;
-                if (batch > 0) {   // (uniform) the previous batch may have left either array dirty
-                    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
-                        cmin[i] = kDeadKey;
-                        cmin2[i] = kDeadKey;
-                    }
-                }
                 if (threadIdx.x == 0) {
                     s_count2[0] = 0u;
                     s_count2[1] = 0u;
@@ -455,8 +440,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                 uint32_t m = src_n;           // live candidates entering the round
                 const uint64_t *cur = src;    // round 0 walks the candidate slot itself (or the prepared first range)
                 for (int round = 0;; ++round) {
-                    // (a round's output is never longer than its input)
-                    uint64_t *nxt = (m <= p.smem_list) ? slist + (round & 1) * p.smem_list : ((round & 1) ? list_b : list_a);
+                    uint64_t *nxt = (round & 1) ? list_b : list_a;
                     uint32_t *nxt_count = &s_count2[round & 1];
                     const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
                     for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
@@ -476,7 +460,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             } else {
                                 live = !near_kept(cells, pitch, c, x, y, d);
                             }
-                            if (live) atomicMin(cm + c, static_cast<unsigned long long>(key));
+                            if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                         }
                         list_push(live, key, nxt, nxt_count);
                     }
@@ -487,9 +471,8 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                         // more live candidates than cells (the first rounds): the cells' minima ARE the candidates that can win, so the
                         // winners come from one pass over the cell grid in shared memory instead of a second pass over the live list
                         for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
-                            cm_old[c] = kDeadKey;
-                            const uint64_t key = cm[c];
-                            if (key == kDeadKey || key >= neighbour_min(cm, pitch, c)) continue;
+                            const uint64_t key = cmin[c];
+                            if (key == kDeadKey || key >= neighbour_min(cmin, pitch, c)) continue;
                             const uint32_t slot = atomicAdd(&s_kept, 1u);
                             if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
                             cells[c] = key_xy(key);
@@ -499,20 +482,18 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             const uint64_t key = nxt[i];
                             const uint32_t xy = key_xy(key);
                             const int c = cell_of(xy);
-                            if (uint64_t(cm[c]) != key) continue;
-                            if (key < neighbour_min(cm, pitch, c)) {
+                            if (uint64_t(cmin[c]) != key) continue;
+                            if (key < neighbour_min(cmin, pitch, c)) {
                                 const uint32_t slot = atomicAdd(&s_kept, 1u);
                                 if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
                                 cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
                             }
                         }
-                        for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cm_old[i] = kDeadKey;
                     }
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
                     if (threadIdx.x == 0) s_count2[(round + 1) & 1] = 0u;
                     cur = nxt;
-                    unsigned long long *t = cm;
-                    cm = cm_old;
-                    cm_old = t;
                     __syncthreads();
                 }
             }
@@ -562,28 +543,12 @@ cudaError_t launch_segment_sort(uint64_t *keys, const uint32_t *counts, int64_t 
     return cudaGetLastError();
 }
 
-// cmin (8) + kept point (4) + [list start (4, one extra entry) + round stamp (2) | second array of minima (8, 8-aligned)] per cell
-size_t select_cell_bytes(int cells_x, int cells_y) {
+size_t select_cell_bytes(int cells_x, int cells_y) {   // cmin (8) + kept point (4) + list start (4, one extra entry) + round stamp (2) per cell
     const size_t n = size_t(cells_x + 2) * (cells_y + 2);
-    return (n * 20 + 8 + 15) & ~size_t(15);
+    return (n * 18 + 4 + 15) & ~size_t(15);
 }
 
-size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_cell_bytes(a.cells_x, a.cells_y) + size_t(a.smem_list) * 16 : 0; }
-
-// Entries per shared-memory live list: what is left of an SM's shared memory once the CTAs that were resident anyway have their cell state.
-uint32_t select_smem_list(const SelectArgs &a) {
-    if (!a.cells_in_smem) return 0u;
-    const size_t cells = select_cell_bytes(a.cells_x, a.cells_y), fixed = 10 * 1024, sm = 227 * 1024;   // fixed: the kernel's static arrays + the per-CTA reserve
-    size_t per_cta;
-    if (a.n_frames <= 148) {
-        per_cta = 176 * 1024;   // a CTA has its SM to itself
-    } else {
-        const size_t resident = std::max<size_t>(1, std::min<size_t>(2048 / SELECT_THREADS, sm / (cells + fixed)));
-        per_cta = sm / resident;
-    }
-    if (per_cta <= cells + fixed) return 0u;
-    return uint32_t(std::min<size_t>((per_cta - cells - fixed) / 16, 8192)) & ~31u;
-}
+size_t select_smem_bytes(const SelectArgs &a) { return a.cells_in_smem ? select_cell_bytes(a.cells_x, a.cells_y) : 0; }
 
 namespace {
 dim3 prepare_grid(int n_frames) { return dim3(unsigned(std::max(1, 4 * 148 / std::max(n_frames, 1))), unsigned(n_frames)); }
