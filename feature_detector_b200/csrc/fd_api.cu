@@ -550,6 +550,7 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
         a.cell_stride = int64_t(cell_bytes);
     }
     a.kept_capacity = a.cells_x * a.cells_y;   // at most one kept point per cell
+    a.few_frames = fv.n_frames <= ctx->sm_count;
     FD_TRY(reserve(ctx, ctx->alive, size_t(fv.n_frames) * capacity * 16));
     FD_TRY(reserve(ctx, ctx->kept, size_t(fv.n_frames) * a.kept_capacity * 8));
     a.live_scratch = static_cast<uint64_t *>(ctx->alive.ptr);

@@ -107,6 +107,10 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
 constexpr int SELECT_THREADS = 512;        // per-frame CTA when the cell grid fits shared memory (256 and 1024 threads measured: slower overall)
 constexpr int SELECT_MAX_THREADS = 1024;   // ... and when it lives in global memory (very fine grids: thousands of cells per round)
+#ifndef FD_SELECT_RANK_COUNT_MAX
+#define FD_SELECT_RANK_COUNT_MAX 256
+#endif
+constexpr int SELECT_RANK_COUNT_MAX = FD_SELECT_RANK_COUNT_MAX;   // kept points ordered by counting smaller keys up to this many, by a bitonic network beyond
 constexpr int SELECT_SORT_SMEM = 1024;    // kept points sorted in shared memory up to this many
 constexpr int SELECT_CELLS_MIN = 65536;   // frames with more candidates than this group them by cell and run the rounds per cell
 constexpr int SELECT_PREFIX_MIN = 8192;   // frames with more candidates than this run the rounds on a rank prefix first
@@ -135,6 +139,7 @@ struct SelectArgs {
     int cells_x, cells_y;           // grid of (min_distance+1)-sided cells
     uint32_t cell_magic;            // ceil(2^32 / (min_distance+1))
     int cells_in_smem;
+    int few_frames;                 // no more frames than SMs: the launch is latency-bound (one CTA or cluster per SM group), not throughput-bound
     uint32_t *overflow_flag;        // set to 1 if any frame's candidate count exceeded cand_capacity
     MaskView mask;                  // candidates on masked-out pixels are never accepted (feature_point_detector.cpp:66)
     uint32_t *pre_hist;             // optional (few frames, many candidates): n_frames * 2048 rank-histogram bins, zero on entry ...

@@ -39,6 +39,32 @@
 // used when the caller asks for the sorted candidate list on the device.
 #include "fd_select_common.cuh"
 
+#ifdef FD_SELECT_TRACE
+// Debug build only (make EXTRA=-DFD_SELECT_TRACE): clock64 stamps of frame 0's CTA at the phase boundaries of select_kernel,
+// read back by fd_debug_select_trace (tools/exp_select_trace.py).  Not part of the shipped library.
+__device__ long long g_select_trace[256];
+__device__ int g_select_trace_n;
+#define SELECT_STAMP(tag)                                                                     \
+    do {                                                                                      \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && g_select_trace_n < 127) {                  \
+            g_select_trace[2 * g_select_trace_n] = clock64();                                 \
+            g_select_trace[2 * g_select_trace_n + 1] = (tag);                                 \
+            ++g_select_trace_n;                                                               \
+        }                                                                                     \
+    } while (0)
+extern "C" int fd_debug_select_trace(long long *out, int max_pairs) {
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_select_trace_n, sizeof(int));
+    n = n < max_pairs ? n : max_pairs;
+    cudaMemcpyFromSymbol(out, g_select_trace, size_t(n) * 16);
+    int zero = 0;
+    cudaMemcpyToSymbol(g_select_trace_n, &zero, sizeof(int));
+    return n;
+}
+#else
+#define SELECT_STAMP(tag) do { } while (0)
+#endif
+
 namespace fdb {
 
 namespace {
@@ -178,6 +204,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
         return (cy + 1) * pitch + cx + 1;
     };
 
+    SELECT_STAMP(1);
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
         cells[i] = kEmptyCell;
         cmin[i] = kDeadKey;
@@ -185,6 +212,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     }
     if (threadIdx.x == 0) s_kept = 0u;
     __syncthreads();
+    SELECT_STAMP(2);
 
     if (first_range_only && (d < 0 || n <= uint32_t(SELECT_PREFIX_MIN))) {   // needs the frame's full key slot: leave it to the flagged launch
         if (threadIdx.x == 0) p.need_more[frame] = 1;
@@ -446,8 +474,13 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
                         bool live = i < m;
                         uint64_t key = 0ull;
+                        SELECT_STAMP(40);
                         if (live) {
                             key = cur[i];
+#ifdef FD_SELECT_TRACE
+                            key = __shfl_sync(__activemask(), key, lane_id());
+                            SELECT_STAMP(41);
+#endif
                             const uint32_t xy = key_xy(key);
                             const int x = int(xy & 0xFFFFu), y = int(xy >> 16);
                             const int c = cell_of(xy);
@@ -460,41 +493,55 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             } else {
                                 live = !near_kept(cells, pitch, c, x, y, d);
                             }
+#ifdef FD_SELECT_TRACE
+                            live = __shfl_sync(__activemask(), int(live), lane_id()) != 0;
+                            SELECT_STAMP(42);
+#endif
                             if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                         }
+                        SELECT_STAMP(43);
                         list_push(live, key, nxt, nxt_count);
+                        SELECT_STAMP(44);
                     }
+                    SELECT_STAMP(45);
                     __syncthreads();
+                    SELECT_STAMP(10);
                     m = *nxt_count;
                     if (m == 0u) break;
+                    // (a round's winners -- dozens in the first rounds -- take their kept-list slots a warp at a time: one shared-memory
+                    // atomic per warp, not per winner; at most one point is ever kept per cell, so the list cannot overflow)
                     if (m > uint32_t(n_cells)) {
                         // more live candidates than cells (the first rounds): the cells' minima ARE the candidates that can win, so the
                         // winners come from one pass over the cell grid in shared memory instead of a second pass over the live list
-                        for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
-                            const uint64_t key = cmin[c];
-                            if (key == kDeadKey || key >= neighbour_min(cmin, pitch, c)) continue;
-                            const uint32_t slot = atomicAdd(&s_kept, 1u);
-                            if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                            cells[c] = key_xy(key);
+                        for (int c0 = 0; c0 < n_cells; c0 += blockDim.x) {
+                            const int c = c0 + int(threadIdx.x);
+                            uint64_t key = kDeadKey;
+                            if (c < n_cells) key = cmin[c];
+                            const bool win = key != kDeadKey && key < neighbour_min(cmin, pitch, c);
+                            if (win) cells[c] = key_xy(key);
+                            list_push(win, key, kept, &s_kept);
                         }
                     } else {
-                        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                            const uint64_t key = nxt[i];
-                            const uint32_t xy = key_xy(key);
-                            const int c = cell_of(xy);
-                            if (uint64_t(cmin[c]) != key) continue;
-                            if (key < neighbour_min(cmin, pitch, c)) {
-                                const uint32_t slot = atomicAdd(&s_kept, 1u);
-                                if (slot < uint32_t(p.kept_capacity)) kept[slot] = key;
-                                cells[c] = xy;   // read by the next round (after the barrier below): covers the winner itself too
+                        for (uint32_t i0 = 0; i0 < m; i0 += blockDim.x) {
+                            const uint32_t i = i0 + threadIdx.x;
+                            uint64_t key = kDeadKey;
+                            bool win = false;
+                            if (i < m) {
+                                key = nxt[i];
+                                const int c = cell_of(key_xy(key));
+                                win = uint64_t(cmin[c]) == key && key < neighbour_min(cmin, pitch, c);
+                                if (win) cells[c] = key_xy(key);   // read by the next round (after the barrier below): covers the winner itself too
                             }
+                            list_push(win, key, kept, &s_kept);
                         }
                     }
                     __syncthreads();
+                    SELECT_STAMP(11);
                     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
                     if (threadIdx.x == 0) s_count2[(round + 1) & 1] = 0u;
                     cur = nxt;
                     __syncthreads();
+                    SELECT_STAMP(12);
                 }
             }
             // enough kept points (or every candidate admitted): done.  Otherwise admit the next, four times larger, rank range;
@@ -506,28 +553,56 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
         }
     }
 
+    SELECT_STAMP(30);
     // ---- order the kept points by rank and cut at the number the reference would have pushed ----
     __syncthreads();
     const uint32_t n_kept = min(s_kept, uint32_t(p.kept_capacity));
-    if (n_kept <= uint32_t(SELECT_SORT_SMEM)) {
-        for (uint32_t i = threadIdx.x; i < n_kept; i += blockDim.x) s_sort[i] = kept[i];
-        __syncthreads();
-        block_bitonic_sort(s_sort, n_kept);
-        kept = s_sort;
-    } else {
-        block_bitonic_sort(kept, n_kept);
-    }
-    __syncthreads();
     uint32_t want = (p.needed > n_pre) ? (p.needed - n_pre) : 1u;  // pushed, then tested: at least one
     want = min(want, uint32_t(p.kp_capacity));
     const uint32_t n_out = min(n_kept, want);
     float4 *kp_out = p.keypoints + int64_t(frame) * p.kp_capacity;
-    for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
-        const uint64_t key = kept[i];
-        const uint32_t xy = key_xy(key);
-        kp_out[i] = make_float4(float(xy & 0xFFFFu), float(xy >> 16), cand_key_response(key), 0.0f);  // Vec2(pixel.x(), pixel.y()), :67
+    if (p.few_frames && n_kept <= uint32_t(SELECT_RANK_COUNT_MAX)) {
+        // Few frames (a CTA has its SM to itself, what counts is latency) and up to a few hundred distinct keys: a key's place in
+        // the order is the number of smaller keys, counted by 2 to 32 lanes per key, and the points that make the cut go straight to
+        // their output slots.  One barrier where the bitonic network takes dozens (5 us for 128 keys); its n^2 comparisons are more
+        // instructions than the network's, which is what counts when the SMs are full of other frames' CTAs.
+        for (uint32_t i = threadIdx.x; i < n_kept; i += blockDim.x) s_sort[i] = kept[i];
+        __syncthreads();
+        SELECT_STAMP(31);
+        uint32_t team = 1u;   // lanes per key
+        while (team < 32u && n_kept * team * 2u <= blockDim.x) team <<= 1;
+        const uint32_t rounded = (n_kept * team + 31u) & ~31u;   // whole warps take part in the shuffles
+        for (uint32_t t = threadIdx.x; t < rounded; t += blockDim.x) {
+            const uint32_t i = t / team, part = t % team;
+            const uint64_t key = i < n_kept ? s_sort[i] : 0ull;
+            uint32_t place = 0u;
+            if (i < n_kept)
+                for (uint32_t j = part; j < n_kept; j += team) place += s_sort[j] < key;
+            for (uint32_t o = 1u; o < team; o <<= 1) place += __shfl_xor_sync(0xffffffffu, place, o);
+            if (i < n_kept && part == 0u && place < n_out) {
+                const uint32_t xy = key_xy(key);
+                kp_out[place] = make_float4(float(xy & 0xFFFFu), float(xy >> 16), cand_key_response(key), 0.0f);  // Vec2(pixel.x(), pixel.y()), :67
+            }
+        }
+    } else {
+        if (n_kept <= uint32_t(SELECT_SORT_SMEM)) {
+            for (uint32_t i = threadIdx.x; i < n_kept; i += blockDim.x) s_sort[i] = kept[i];
+            __syncthreads();
+            block_bitonic_sort(s_sort, n_kept);
+            kept = s_sort;
+        } else {
+            block_bitonic_sort(kept, n_kept);
+        }
+        __syncthreads();
+        SELECT_STAMP(31);
+        for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+            const uint64_t key = kept[i];
+            const uint32_t xy = key_xy(key);
+            kp_out[i] = make_float4(float(xy & 0xFFFFu), float(xy >> 16), cand_key_response(key), 0.0f);
+        }
     }
     if (threadIdx.x == 0) p.kp_counts[frame] = int32_t(n_out);
+    SELECT_STAMP(32);
 }
 
 }  // namespace
