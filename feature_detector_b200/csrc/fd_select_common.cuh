@@ -45,15 +45,20 @@ __device__ __forceinline__ uint64_t neighbour_min(const unsigned long long *cmin
     return best;
 }
 
-// Unordered append of this thread's surviving candidate key to a list (warp-aggregated counter bump).
+// Unordered append of this thread's surviving candidate key to a list (warp-aggregated counter bump).  Whole warps only: every
+// caller rounds its loop bounds to warps, which spares the active-mask vote and the leader election of the general form.
+__device__ __forceinline__ uint32_t lane_mask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
 __device__ __forceinline__ void list_push(bool keep, uint64_t value, uint64_t *list, uint32_t *counter) {
-    const uint32_t m = __ballot_sync(__activemask(), keep);
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
     if (m == 0u) return;
-    const int leader = __ffs(m) - 1;
     uint32_t base = 0u;
-    if (lane_id() == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(__activemask(), base, leader);
-    if (keep) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
+    if (lane_id() == 0) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(m & lane_mask_lt())] = value;
 }
 
 // Exclusive prefix sum of one value per thread over the whole CTA (up to 1024 threads).
