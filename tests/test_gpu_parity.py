@@ -856,6 +856,16 @@ def test_one_call_host_to_host_equals_the_separate_calls(ctx, checker):
             kp, cnt, desc = ctx.detect_describe_host(batch, det, None, 200)
             assert desc is None and np.array_equal(cnt, cnt_ref) and np.array_equal(kp[0, :cnt[0]], kp_ref[0, :cnt[0]])
     ctx.set_existing_features([])
+    # results of more than 1 MB leave by strided copies instead of the packed block
+    many, det_many = np.concatenate([frames] * 8), fd.DetectParams(fd.FAST, 10.0, 5, 1000, fast_n=9)
+    ctx.upload(many)
+    ctx.detect(det_many)
+    ctx.describe_selected(brief)
+    (kp_ref, cnt_ref), desc_ref = ctx.keypoints(1000), ctx.descriptors(1000)
+    kp, cnt, desc = ctx.detect_describe_host(many, det_many, brief, 1000)
+    assert len(many) * 1000 * 48 > (1 << 20) and np.array_equal(cnt, cnt_ref) and cnt.max() > 400
+    for f in range(len(many)):
+        assert np.array_equal(kp[f, :cnt[f]], kp_ref[f, :cnt[f]]) and np.array_equal(desc[f, :cnt[f]], desc_ref[f, :cnt[f]])
     o = checker.detect(FAST, frames[0], 10.0, 20, 200, fast_n=9)
     kp, cnt, _ = ctx.detect_describe_host(frames[0], det, brief, 200)
     assert np.array_equal(np.stack([kp["x"][0, :cnt[0]], kp["y"][0, :cnt[0]]], 1), o["features"])
