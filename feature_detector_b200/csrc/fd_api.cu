@@ -1062,6 +1062,7 @@ fd_status fd_detect_describe_host(fd_context *ctx, const uint8_t *host_frames, i
             static_cast<const uint32_t *>(ctx->flags.ptr), static_cast<const int32_t *>(ctx->kp_counts.ptr), static_cast<const uint4 *>(ctx->kp.ptr), ctx->kp_capacity,
             brief ? static_cast<const uint4 *>(ctx->desc.ptr) : nullptr, ctx->desc_capacity, w, n_frames, count_units, static_cast<uint4 *>(ctx->result_pack.ptr));
         FD_CUDA(ctx, cudaGetLastError());
+        ++ctx->launches;
         FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->result_pack.ptr, need, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
         FD_CUDA(ctx, cudaMemcpyAsync(st, ctx->flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
