@@ -105,7 +105,10 @@ cudaError_t launch_corner_tma(const CornerArgs &args, const void *tensor_map, in
 // ---- kernel 3: per-frame sort + greedy min-distance selection ----------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_MAX_KEYS = 8192;  // 64 KiB of keys per CTA -> three sorting CTAs per SM
-constexpr int SELECT_THREADS = 512;        // per-frame CTA when the cell grid fits shared memory (256 and 1024 threads measured: slower overall)
+#ifndef FD_SELECT_THREADS
+#define FD_SELECT_THREADS 512
+#endif
+constexpr int SELECT_THREADS = FD_SELECT_THREADS;        // per-frame CTA when the cell grid fits shared memory (256 and 1024 threads measured: slower overall)
 constexpr int SELECT_MAX_THREADS = 1024;   // ... and when it lives in global memory (very fine grids: thousands of cells per round)
 #ifndef FD_SELECT_RANK_COUNT_MAX
 #define FD_SELECT_RANK_COUNT_MAX 256
