@@ -471,6 +471,9 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     uint64_t *nxt = (round & 1) ? list_b : list_a;
                     uint32_t *nxt_count = &s_count2[round & 1];
                     const uint32_t rounded = (m + 31u) & ~31u;   // whole warps enter list_push together
+                    // the first round of an unfiltered frame (no rank range, no mask) keeps every candidate alive: its output list would be
+                    // a copy of its input, so nothing is pushed and the next round walks the candidate slot again
+                    const bool all_live = round == 0 && batch == 0 && mb == nullptr && limit == kDeadKey;
                     for (uint32_t i = threadIdx.x; i < rounded; i += blockDim.x) {
                         bool live = i < m;
                         uint64_t key = 0ull;
@@ -500,13 +503,14 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             if (live) atomicMin(cmin + c, static_cast<unsigned long long>(key));
                         }
                         SELECT_STAMP(43);
-                        list_push(live, key, nxt, nxt_count);
+                        if (!all_live) list_push(live, key, nxt, nxt_count);
                         SELECT_STAMP(44);
                     }
                     SELECT_STAMP(45);
                     __syncthreads();
                     SELECT_STAMP(10);
-                    m = *nxt_count;
+                    const uint64_t *alive = all_live ? cur : nxt;   // the candidates entering the next round
+                    if (!all_live) m = *nxt_count;
                     if (m == 0u) break;
                     // (a round's winners -- dozens in the first rounds -- take their kept-list slots a warp at a time: one shared-memory
                     // atomic per warp, not per winner; at most one point is ever kept per cell, so the list cannot overflow)
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                             uint64_t key = kDeadKey;
                             bool win = false;
                             if (i < m) {
-                                key = nxt[i];
+                                key = alive[i];
                                 const int c = cell_of(key_xy(key));
                                 win = uint64_t(cmin[c]) == key && key < neighbour_min(cmin, pitch, c);
                                 if (win) cells[c] = key_xy(key);   // read by the next round (after the barrier below): covers the winner itself too
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
                     SELECT_STAMP(11);
                     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cmin[i] = kDeadKey;
                     if (threadIdx.x == 0) s_count2[(round + 1) & 1] = 0u;
-                    cur = nxt;
+                    cur = alive;
                     __syncthreads();
                     SELECT_STAMP(12);
                 }
