@@ -935,3 +935,36 @@ def test_describe_selected_refuses_keypoints_of_other_frames(ctx, torch_cuda):
     assert e.value.status == 6                                          # FD_ERR_NOT_READY
     ctx.detect(prm)
     ctx.describe_selected(fd.BriefParams(256, 8))                      # and usable again after a detect over the bound frames
+
+
+@pytest.mark.parametrize("shape", [(7, 65535), (65535, 7), (9, 40000), (40000, 9), (23, 16389)])
+def test_extreme_shapes_vs_checker(ctx, checker, shape):
+    """Frames at the coordinate limit of the candidate keys (65535 rows or columns: 16 bits each) and with extreme aspect ratios --
+    row pitches that are and are not multiples of 16 (the TMA paths need the former), thousands of column strips, bands of a few
+    rows -- against the checker: candidates, keypoints, the LSD field and BRIEF descriptors near the far corner."""
+    h, w = shape
+    rng = np.random.default_rng(h * 131 + w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    im = (96 + 64 * (((yy // 3) + (xx // 5)) % 2) + rng.integers(0, 24, (h, w))).astype(np.uint8)
+    for name, thr, d, n, fast_n in (("fast", 10.0, 20, 200, 9), ("harris", 30.0, 20, 200, 12), ("shi", 40.0, 3, 500, 12)):
+        o = checker.detect(KIND[name], im, thr, d, n, fast_n=fast_n)
+        feats, cand, kp = _gpu_detect(ctx, im, KIND[name], thr, d, n, fast_n)
+        _assert_same_candidates(cand, o)
+        _assert_same_features(feats, cand, o, im.shape, d, n)
+        assert o["n_cand"] > 0, (name, shape)
+    # descriptors of the keypoints closest to the last row / column
+    ctx.describe_selected(fd.BriefParams(256, 8))
+    bits = fd.unpack_bits(ctx.descriptors(500)[0, :len(feats)], 256)
+    far = np.argsort(-(feats[:, 0] + feats[:, 1]))[:20]
+    ok, exp = checker.brief(im, feats[far], 256, 8)
+    assert ok and np.array_equal(bits[far], exp)
+    ctx.upload(im)
+    ctx.lsd_field(fd.LsdParams(20.0, 1))
+    g = ctx.lsd_download(0)
+    o = checker.lsd_map(im)
+    assert np.array_equal(g["norm"][:h - 1, :w - 1].view(np.uint32), o["norm"].view(np.uint32))
+    valid = g["norm"][:h - 1, :w - 1] > 20.0
+    assert np.array_equal(valid, o["valid"].astype(bool)) and g["n_valid"] == int(o["valid"].sum())
+    assert np.max(np.abs(g["angle"][:h - 1, :w - 1][valid] - o["angle"][valid]), initial=0.0) <= 1e-5
+    exp_rc = o["sorted_rc"]
+    assert np.array_equal(g["norm"].reshape(-1)[g["sorted_idx"]], o["norm"][exp_rc[:, 0], exp_rc[:, 1]])
