@@ -31,7 +31,7 @@ def main():
 
     dev = torch.device("cuda", 0)
     quick = os.environ.get("SANITIZE_QUICK") == "1"   # racecheck is two orders of magnitude slower than memcheck: small frames only
-    shapes = [(333, 217, 3), (752, 480, 2), (64, 40, 2), (131, 9, 1)]   # (cols, rows, frames); odd widths, a sliver
+    shapes = [(333, 217, 3), (752, 480, 2), (64, 40, 2), (131, 9, 1), (65535, 7, 1), (7, 65535, 1)]   # (cols, rows, frames); odd widths, a sliver, the coordinate limit both ways
     if quick:
         shapes = [(333, 217, 2), (64, 40, 2), (131, 9, 1)]
     done = []
