@@ -127,6 +127,8 @@ def load_library():
                                                   C.POINTER(C.c_float)]),
         "fd_lsd_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fd_lsd_download": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int64, i32p]),
+        "fd_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+        "fd_host_free": (C.c_int, [vp]),
         "fd_detect_describe_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.POINTER(BriefParams), C.c_int, vp, i32p, vp, C.c_int]),
         "fd_match_consecutive": (C.c_int, [vp]),
         "fd_match_descriptors": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]),

@@ -6,6 +6,13 @@
 
 namespace feature_detector {
 
+void *LineLevelAngleField::AllocHost(size_t bytes) {
+    void *p = nullptr;
+    return fd_host_alloc(&p, bytes) == FD_OK ? p : nullptr;
+}
+
+void LineLevelAngleField::FreeHost(void *ptr) { fd_host_free(ptr); }
+
 LineLevelAngleField::~LineLevelAngleField() {
     if (ctx_ != nullptr) fd_destroy(ctx_);
 }
@@ -24,9 +31,13 @@ bool LineLevelAngleField::Compute(const GrayImage &image) {
     rows_ = image.rows();
     cols_ = image.cols();
     const size_t px = size_t(rows_) * size_t(cols_);
-    norm_.resize(px);
-    angle_.resize(px);
-    seeds_.resize(px);
+    if (!norm_.reserve(px) || !angle_.reserve(px) || !seeds_.reserve(px)) {
+        last_error_ = "fd_host_alloc failed";
+        return false;
+    }
+    norm_.set_size(px);
+    angle_.set_size(px);
+    seeds_.set_size(0);
     fd_lsd_params p = {};
     p.min_valid_gradient_norm = options_.kMinValidGradientNorm;
     p.want_sorted = 1;
@@ -36,7 +47,7 @@ bool LineLevelAngleField::Compute(const GrayImage &image) {
         last_error_ = fd_last_error(ctx_);
         return false;
     }
-    seeds_.resize(size_t(n_valid));
+    seeds_.set_size(size_t(n_valid));
     return true;
 }
 

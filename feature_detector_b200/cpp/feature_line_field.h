@@ -25,6 +25,37 @@ namespace feature_detector {
 
 class LineLevelAngleField {
 public:
+    // A page-locked array that only ever grows and is never initialised: the maps come back from the GPU 16 bytes per pixel on
+    // every call, which from pageable memory costs five times the copy itself (fd_host_alloc, include/fd_b200.h).
+    template <typename T>
+    class HostArray {
+    public:
+        HostArray() = default;
+        ~HostArray() { LineLevelAngleField::FreeHost(data_); }
+        HostArray(const HostArray &) = delete;
+        HostArray &operator=(const HostArray &) = delete;
+        bool reserve(size_t n) {   // contents are lost when the array has to grow
+            if (n <= capacity_) return true;
+            LineLevelAngleField::FreeHost(data_);
+            data_ = static_cast<T *>(LineLevelAngleField::AllocHost(n * sizeof(T)));
+            capacity_ = data_ != nullptr ? n : 0;
+            size_ = 0;
+            return data_ != nullptr;
+        }
+        void set_size(size_t n) { size_ = n; }
+        size_t size() const { return size_; }
+        bool empty() const { return size_ == 0; }
+        const T *data() const { return data_; }
+        T *data() { return data_; }
+        const T &operator[](size_t i) const { return data_[i]; }
+        const T *begin() const { return data_; }
+        const T *end() const { return data_ + size_; }
+
+    private:
+        T *data_ = nullptr;
+        size_t size_ = 0, capacity_ = 0;
+    };
+
     struct Options {
         float kMinValidGradientNorm = 20.0f;  // feature_line_detector.h:41
     };
@@ -44,9 +75,9 @@ public:
     // seeds are row * image_cols + col of the valid pixels, norm descending, ties in the reference's push order.
     int32_t image_rows() const { return rows_; }
     int32_t image_cols() const { return cols_; }
-    const std::vector<float> &gradient_norm() const { return norm_; }
-    const std::vector<float> &line_level_angle() const { return angle_; }
-    const std::vector<int32_t> &sorted_seeds() const { return seeds_; }
+    const HostArray<float> &gradient_norm() const { return norm_; }
+    const HostArray<float> &line_level_angle() const { return angle_; }
+    const HostArray<int32_t> &sorted_seeds() const { return seeds_; }
 
     // Leave `pixels` (Eigen::Matrix<PixelParam, Dynamic, Dynamic>) and `sorted` (std::vector<PixelParam *>) as the
     // reference's ComputeLineLevelAngleMap leaves pixels_ and sorted_pixels_, including what it does NOT touch:
@@ -120,8 +151,10 @@ public:
 private:
     Options options_;
     int32_t rows_ = 0, cols_ = 0;
-    std::vector<float> norm_, angle_;
-    std::vector<int32_t> seeds_;
+    static void *AllocHost(size_t bytes);   // fd_host_alloc / fd_host_free (feature_line_field.cpp)
+    static void FreeHost(void *ptr);
+    HostArray<float> norm_, angle_;
+    HostArray<int32_t> seeds_;
     int device_ = 0;
     fd_context *ctx_ = nullptr;
     std::string last_error_;

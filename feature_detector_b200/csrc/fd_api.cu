@@ -1450,6 +1450,22 @@ fd_status fd_lsd_device_outputs(fd_context *ctx, const float **dev_norm, const f
     return FD_OK;
 }
 
+fd_status fd_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return FD_ERR_INVALID_ARGUMENT;
+    *ptr = nullptr;
+    const cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        *ptr = nullptr;
+        return e == cudaErrorMemoryAllocation ? FD_ERR_OUT_OF_MEMORY : FD_ERR_CUDA;
+    }
+    return FD_OK;
+}
+
+fd_status fd_host_free(void *ptr) {
+    if (ptr == nullptr) return FD_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? FD_OK : FD_ERR_CUDA;
+}
+
 fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *host_angle, int32_t *host_sorted_idx, int64_t sorted_capacity,
                           int32_t *host_n_valid) {
     if (!ctx) return FD_ERR_INVALID_ARGUMENT;

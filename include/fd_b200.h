@@ -225,6 +225,13 @@ fd_status fd_device_descriptors(fd_context *ctx, const uint8_t **dev_desc, int *
 fd_status fd_descriptors_as_float(fd_context *ctx, float *dev_out);
 fd_status fd_download_descriptors_float(fd_context *ctx, float *host_desc, int kp_capacity);
 
+/* ---- page-locked host memory (no reference counterpart) ------------------------------------------ */
+/* Buffers that cross the bus on every call -- the LSD maps a drop-in class downloads (16 bytes per pixel), frames a caller
+ * uploads -- move at the link's speed only from page-locked memory; from pageable memory the driver stages them at a fifth of it.
+ * fd_host_alloc returns cudaMallocHost memory (FD_ERR_OUT_OF_MEMORY when the host refuses), fd_host_free releases it. */
+fd_status fd_host_alloc(void **ptr, size_t bytes);
+fd_status fd_host_free(void *ptr);
+
 /* ---- kernel 5: FeatureLineDetector::ComputeLineLevelAngleMap (feature_line_detector.cpp:56-97) -- */
 /* For every bound frame: gradient norm and level-line angle maps, written as rows x cols floats, row-major
  * (the reference's pixels_ is (rows-1) x (cols-1); the extra last row / column is zero, which keeps every

@@ -7,6 +7,7 @@
 // about the CUDA kernels -- the gpu-marked tests do that against the real library -- and the product has no such path:
 // libfd_b200.so fails with FD_ERR_NO_DEVICE without a GPU (tests/test_abi.py::test_no_cpu_fallback_without_device).
 // Only the entry points the drop-in classes call are provided; one frame per call is enough for them.
+#include <cstdlib>
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -179,6 +180,15 @@ fd_status fd_lsd_download(fd_context *ctx, int frame, float *host_norm, float *h
         std::copy(ctx->seeds.begin(), ctx->seeds.end(), host_sorted_idx);
     }
     if (host_n_valid) *host_n_valid = int32_t(ctx->seeds.size());
+    return FD_OK;
+}
+
+fd_status fd_host_alloc(void **ptr, size_t bytes) {
+    *ptr = std::malloc(bytes ? bytes : 16);
+    return *ptr ? FD_OK : FD_ERR_OUT_OF_MEMORY;
+}
+fd_status fd_host_free(void *ptr) {
+    std::free(ptr);
     return FD_OK;
 }
 

@@ -25,6 +25,8 @@ static std::vector<int32_t> g_seed_override;   // (row, col) pairs, empty = keep
 namespace feature_detector {
 
 LineLevelAngleField::~LineLevelAngleField() {}
+void *LineLevelAngleField::AllocHost(size_t bytes) { return std::malloc(bytes ? bytes : 1); }   // no GPU here: plain memory
+void LineLevelAngleField::FreeHost(void *ptr) { std::free(ptr); }
 
 bool LineLevelAngleField::Compute(const GrayImage &image) {
     if (image.data() == nullptr || image.rows() < 2 || image.cols() < 2) return false;
@@ -39,19 +41,23 @@ bool LineLevelAngleField::Compute(const GrayImage &image) {
                     int64_t(pr) * pc, &n_sorted) != 1)
         return false;
     // the library's layout: rows x cols maps with a zero last row / column, seeds as row * cols + col
-    norm_.assign(size_t(rows_) * cols_, 0.0f);
-    angle_.assign(size_t(rows_) * cols_, 0.0f);
+    const size_t px = size_t(rows_) * cols_;
+    if (!norm_.reserve(px) || !angle_.reserve(px) || !seeds_.reserve(px)) return false;
+    norm_.set_size(px);
+    angle_.set_size(px);
+    std::fill(norm_.data(), norm_.data() + px, 0.0f);
+    std::fill(angle_.data(), angle_.data() + px, 0.0f);
     for (int32_t r = 0; r < pr; ++r)
         for (int32_t c = 0; c < pc; ++c) {
-            norm_[size_t(r) * cols_ + c] = norm[size_t(r) * pc + c];
-            angle_[size_t(r) * cols_ + c] = valid[size_t(r) * pc + c] ? angle[size_t(r) * pc + c] : 0.0f;
+            norm_.data()[size_t(r) * cols_ + c] = norm[size_t(r) * pc + c];
+            angle_.data()[size_t(r) * cols_ + c] = valid[size_t(r) * pc + c] ? angle[size_t(r) * pc + c] : 0.0f;
         }
     if (!g_seed_override.empty()) {
         if (int64_t(g_seed_override.size()) != 2 * n_sorted) return false;   // must be a permutation of the same seeds
         sorted_rc.assign(g_seed_override.begin(), g_seed_override.end());
     }
-    seeds_.resize(size_t(n_sorted));
-    for (int64_t i = 0; i < n_sorted; ++i) seeds_[size_t(i)] = sorted_rc[2 * i] * cols_ + sorted_rc[2 * i + 1];
+    seeds_.set_size(size_t(n_sorted));
+    for (int64_t i = 0; i < n_sorted; ++i) seeds_.data()[size_t(i)] = sorted_rc[2 * i] * cols_ + sorted_rc[2 * i + 1];
     return true;
 }
 
