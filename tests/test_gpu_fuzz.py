@@ -67,3 +67,39 @@ def test_cuda_path_equals_checker_on_random_small_frames(checker):
                 bits = fd.unpack_bits(ctx.descriptors(cap)[0, :len(pts)])
                 assert np.array_equal(bits, checker.brief(img, pts, 256, 8)[1]), case
         ctx.set_existing_features([])
+
+
+def test_cuda_path_equals_checker_on_random_medium_frames(checker):
+    """The same comparison on frames of random size up to 1000 x 700 in batches of one to three: several column strips and row bands,
+    ragged last strips, rank ranges in the selection (thousands of candidates), the per-cell form (FAST at a low threshold)."""
+    import os
+    from feature_detector_b200.synth import synth
+    from oracle.bindings import FAST, HARRIS, SHI_TOMAS
+    kinds = {FAST: fd.FAST, HARRIS: fd.HARRIS, SHI_TOMAS: fd.SHI_TOMAS}
+    rng = np.random.default_rng(int(os.environ.get("FD_FUZZ_SEED", "20261018")) + 1)
+    with fd.Context(0) as ctx:
+        for it in range(int(os.environ.get("FD_FUZZ_MEDIUM_CASES", "60"))):
+            rows, cols, n = int(rng.integers(40, 700)), int(rng.integers(40, 1000)), int(rng.integers(1, 4))
+            if rng.integers(0, 3) == 0:
+                frames = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+            else:
+                frames = np.stack([synth(cols, rows, int(rng.integers(0, 1000))) for _ in range(n)])
+            kind = (FAST, HARRIS, SHI_TOMAS)[int(rng.integers(0, 3))]
+            thr = float(rng.choice([0.1, 5.0, 10.0, 30.0, 40.0, 200.0]))
+            d, needed, fast_n = int(rng.choice([1, 5, 15, 20, 60])), int(rng.choice([1, 50, 200, 1000])), int(rng.choice([9, 12]))
+            case = (it, rows, cols, n, kind, thr, d, needed, fast_n)
+            ctx.upload(frames)
+            ctx.detect(fd.DetectParams(kinds[kind], thr, d, needed, fast_n=fast_n))
+            kp, cnt = ctx.keypoints(needed)
+            for f in range(n):
+                o = checker.detect(kind, frames[f], thr, d, needed, fast_n=fast_n)
+                cand = ctx.candidates(f)
+                assert len(cand) == o["n_cand"], case
+                g = np.lexsort((cand["x"], cand["y"]))
+                c = np.lexsort((o["cand_xy"][:, 0], o["cand_xy"][:, 1]))
+                assert np.array_equal(cand["x"][g], o["cand_xy"][c, 0]) and np.array_equal(cand["y"][g], o["cand_xy"][c, 1]), case
+                assert np.array_equal(cand["response"][g].view(np.uint32), o["cand_resp"][c].view(np.uint32)), case
+                got = np.stack([kp["x"][f, :cnt[f]], kp["y"][f, :cnt[f]]], 1).astype(np.float32)
+                if not np.array_equal(got, o["features"]):
+                    assert len(np.unique(o["cand_resp"])) < len(o["cand_resp"]), case      # only a tie may reorder the walk
+                    assert len(got) == len(o["features"]) or needed > len(got), case
