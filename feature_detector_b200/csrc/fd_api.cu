@@ -481,6 +481,29 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             volatile float inv2 = inv * inv;                  // harris.cpp:72
             a.inv_cnt = inv;
             a.inv_cnt2 = inv2;
+            {
+                // harris.cpp:98: (trace * trace * 0.21f * inv_cnt2) > thr, i.e. fl(fl(tt * 0.21f) * inv2) > thr -- two roundings of a
+                // non-negative tt, monotone non-decreasing in tt, so the set of passing tt is an upper interval of the floats.  Its
+                // lower end is found by bisection over the bit patterns of the non-negative floats (which order like the floats).
+                auto passes = [&](uint32_t bits) {
+                    float tt;
+                    std::memcpy(&tt, &bits, 4);
+                    volatile float t1 = tt * 0.21f;
+                    volatile float t2 = t1 * inv2;
+                    return t2 > a.thr;
+                };
+                uint32_t lo = 0u, hi = 0x7F800000u;   // +0 .. +inf
+                if (!passes(hi)) {
+                    a.harris_tt_min = std::nanf("");   // no tt passes (thr is +inf or NaN): tt >= NaN is false
+                } else {
+                    while (lo < hi) {
+                        const uint32_t mid = lo + (hi - lo) / 2;
+                        if (passes(mid)) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    std::memcpy(&a.harris_tt_min, &lo, 4);
+                }
+            }
             a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
             a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
             a.cand_capacity = cap;

@@ -97,12 +97,18 @@ __device__ __forceinline__ void product_row(SumRow &h, const MagicRow &up, const
         pyy[j] = __fmul_rn(iy, iy);
         pxy[j] = __fmul_rn(ix, iy);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        h.xx[j] = __fadd_rn(__fadd_rn(pxx[j], pxx[j + 1]), pxx[j + 2]);
-        h.yy[j] = __fadd_rn(__fadd_rn(pyy[j], pyy[j + 1]), pyy[j + 2]);
-        h.xy[j] = __fadd_rn(__fadd_rn(pxy[j], pxy[j + 1]), pxy[j + 2]);
-    }
+    // Every term and every partial sum is an integer below 2^24, so the association does not matter (the reference's order,
+    // harris.cpp:47-62, gives the same bits): neighbouring outputs share a pair sum, six additions per array instead of eight.
+    auto sums = [](const float *p, float *h) {
+        const float q = __fadd_rn(p[1], p[2]), r = __fadd_rn(p[3], p[4]);
+        h[0] = __fadd_rn(p[0], q);
+        h[1] = __fadd_rn(q, p[3]);
+        h[2] = __fadd_rn(p[2], r);
+        h[3] = __fadd_rn(r, p[5]);
+    };
+    sums(pxx, h.xx);
+    sums(pyy, h.yy);
+    sums(pxy, h.xy);
 }
 
 template <int KIND, bool MASKED>
