@@ -87,28 +87,27 @@ __device__ __forceinline__ void load_magic_row(MagicRow &r, const uint32_t *row_
 }
 
 // Products of gradient row `mid` (row above `up`, row below `dn`) and their horizontal 3-sums (harris.cpp:36-40, 47-62).
+// Gradients are integers of magnitude <= 255, so every product and every partial sum is an integer below 2^24: exact in fp32
+// whatever the association and whether or not a multiply is fused into the add that consumes it -- the bits are the reference's.
+// Per array: neighbouring outputs share a pair sum and the four products used once ride on an FMA (2 mul + 4 fma + 2 add, not 6 + 8).
 __device__ __forceinline__ void product_row(SumRow &h, const MagicRow &up, const MagicRow &mid, const MagicRow &dn) {
-    float pxx[6], pyy[6], pxy[6];
+    float ix[6], iy[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {  // column c0-1+j  <->  v index j+1
-        const float ix = __fsub_rn(mid.v[j + 2], mid.v[j]);       // harris.cpp:36 (the 2^23 of both operands cancels exactly)
-        const float iy = __fsub_rn(dn.v[j + 1], up.v[j + 1]);     // harris.cpp:37
-        pxx[j] = __fmul_rn(ix, ix);
-        pyy[j] = __fmul_rn(iy, iy);
-        pxy[j] = __fmul_rn(ix, iy);
+        ix[j] = __fsub_rn(mid.v[j + 2], mid.v[j]);       // harris.cpp:36 (the 2^23 of both operands cancels exactly)
+        iy[j] = __fsub_rn(dn.v[j + 1], up.v[j + 1]);     // harris.cpp:37
     }
-    // Every term and every partial sum is an integer below 2^24, so the association does not matter (the reference's order,
-    // harris.cpp:47-62, gives the same bits): neighbouring outputs share a pair sum, six additions per array instead of eight.
-    auto sums = [](const float *p, float *h) {
-        const float q = __fadd_rn(p[1], p[2]), r = __fadd_rn(p[3], p[4]);
-        h[0] = __fadd_rn(p[0], q);
-        h[1] = __fadd_rn(q, p[3]);
-        h[2] = __fadd_rn(p[2], r);
-        h[3] = __fadd_rn(r, p[5]);
+    auto sums = [](const float *a, const float *b, float *out) {   // out[j] = sum over k = j .. j+2 of a[k] * b[k]
+        const float p2 = __fmul_rn(a[2], b[2]), p3 = __fmul_rn(a[3], b[3]);
+        const float q = __fmaf_rn(a[1], b[1], p2), r = __fmaf_rn(a[4], b[4], p3);
+        out[0] = __fmaf_rn(a[0], b[0], q);
+        out[1] = __fadd_rn(q, p3);
+        out[2] = __fadd_rn(p2, r);
+        out[3] = __fmaf_rn(a[5], b[5], r);
     };
-    sums(pxx, h.xx);
-    sums(pyy, h.yy);
-    sums(pxy, h.xy);
+    sums(ix, ix, h.xx);
+    sums(iy, iy, h.yy);
+    sums(ix, iy, h.xy);
 }
 
 template <int KIND, bool MASKED>
