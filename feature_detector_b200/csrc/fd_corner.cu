@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(CORNER_THREADS, 2) corner_kernel(const CornerA
                         const float sxx = __fsub_rn(__int_as_float(ixx), kSumBasePos);
                         const float syy = __fsub_rn(__int_as_float(iyy), kSumBasePos);
                         const float sxy = __fsub_rn(__int_as_float(ixy), kSumBaseMid);
-                        rq[j] = (q_valid && col_valid[j] && ((mnib >> j) & 1u)) ? response_of<KIND>(sxx, syy, sxy, p) : 0.0f;
+                        rq[j] = (q_valid && col_valid[j] && ((mnib >> j) & 1u)) ? response_of<KIND>(sxx, syy, sxy, p, p.thr) : 0.0f;
                     }
                     if (resp_map != nullptr && q >= rb && q < re) {
 #pragma unroll

@@ -164,11 +164,13 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
         issue_group(0, 0);
 
         bool col_valid[4], col_owned[4];
+        float thr_col[4];   // the response threshold per column, +inf where the column has no response (response_of)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + j;
             col_valid[j] = (c >= col_lo && c <= col_hi);
             col_owned[j] = col_valid[j] && (c >= x0 + 1) && (c <= x0 + CORNER_STRIP_OUT);
+            thr_col[j] = col_valid[j] ? p.thr : __int_as_float(0x7f800000);
         }
 
         MagicRow px[3];
@@ -232,13 +234,18 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                             mnib = __funnelshift_r(__ldg(mp), __ldg(mp + 1), c0 & 31) & 0xFu;
                         }
                     }
+                    if (q_valid) {   // (warp-uniform: false only for the halo rows at the ends of a band)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float sxx = __fadd_rn(__fadd_rn(hs[cur].xx[j], hs[p2].xx[j]), hs[p1].xx[j]);  // harris.cpp:81-88,108-116
-                        const float syy = __fadd_rn(__fadd_rn(hs[cur].yy[j], hs[p2].yy[j]), hs[p1].yy[j]);
-                        const float sxy = __fadd_rn(__fadd_rn(hs[cur].xy[j], hs[p2].xy[j]), hs[p1].xy[j]);
-                        const float r = response_of<KIND>(sxx, syy, sxy, p);
-                        rq[j] = (q_valid && col_valid[j] && ((mnib >> j) & 1u)) ? r : 0.0f;
+                        for (int j = 0; j < 4; ++j) {
+                            const float sxx = __fadd_rn(__fadd_rn(hs[cur].xx[j], hs[p2].xx[j]), hs[p1].xx[j]);  // harris.cpp:81-88,108-116
+                            const float syy = __fadd_rn(__fadd_rn(hs[cur].yy[j], hs[p2].yy[j]), hs[p1].yy[j]);
+                            const float sxy = __fadd_rn(__fadd_rn(hs[cur].xy[j], hs[p2].xy[j]), hs[p1].xy[j]);
+                            const float r = response_of<KIND>(sxx, syy, sxy, p, thr_col[j]);
+                            rq[j] = (!MASKED || ((mnib >> j) & 1u)) ? r : 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rq[j] = 0.0f;
                     }
                     if (resp_map != nullptr && q >= rb && q < re) {
 #pragma unroll
