@@ -165,12 +165,14 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
 
         bool col_valid[4], col_owned[4];
         float thr_col[4];   // the response threshold per column, +inf where the column has no response (response_of)
+        float thr_own[4];   // ... and +inf where the column belongs to the neighbouring strip (the candidate test below)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + j;
             col_valid[j] = (c >= col_lo && c <= col_hi);
             col_owned[j] = col_valid[j] && (c >= x0 + 1) && (c <= x0 + CORNER_STRIP_OUT);
             thr_col[j] = col_valid[j] ? p.thr : __int_as_float(0x7f800000);
+            thr_own[j] = col_owned[j] ? p.thr : __int_as_float(0x7f800000);
         }
 
         MagicRow px[3];
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                             const float r = (j == 3) ? right_in : resp[p2][j + 1];
                             // v == 0 means "at or below threshold" (harris.cpp:130); strict 4-neighbour max (:131-132) as one compare against
                             // the largest neighbour (responses are finite, so the four strict compares and this one agree)
-                            const float big = fmaxf(fmaxf(l, r), fmaxf(resp[cur][j], rq[j]));
-                            if (col_owned[j] && v > p.thr && v > big) mine |= 1u << j;
+                            // ... and the threshold (and whether the column is this strip's at all) is a fifth operand of the same maximum
+                            const float big = fmaxf(fmaxf(fmaxf(l, r), resp[cur][j]), fmaxf(rq[j], thr_own[j]));
+                            if (v > big) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
                             // Stage slots: a lane owns up to four candidates, so its count has three bits and the warp's exclusive prefix is
