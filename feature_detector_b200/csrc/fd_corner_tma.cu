@@ -29,7 +29,8 @@ constexpr int CT_WARPS = CORNER_TMA_THREADS / 32;
 constexpr int CT_GROUP_ROWS = CORNER_TMA_GROUP_ROWS;   // rows per TMA box; a multiple of 3 (the register pipeline's period)
 constexpr int CT_SLOTS = 3;                            // ring slots: the group in use, the one before, the one in flight
 constexpr int CT_ROW_WORDS = 40;                       // 160-byte box rows
-constexpr int CT_STAGE = 256;                          // candidate keys staged per warp (a row adds at most 128)
+constexpr int CT_LANE_SLOTS = 16;                     // candidate keys each lane can stage between flushes (a row adds at most 4)
+constexpr int CT_STAGE = 32 * CT_LANE_SLOTS;           // ... per warp: entry k of lane l sits at stage[32 k + l]
 constexpr uint32_t CT_GROUP_BYTES = CT_GROUP_ROWS * CT_ROW_WORDS * 4;
 static_assert(CT_GROUP_ROWS % 3 == 0 && CT_GROUP_ROWS >= 3, "group rows must be a multiple of the pipeline period");
 
@@ -190,16 +191,26 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
         }
         uint32_t *counter = p.cand_counts + frame;
         uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
-        uint32_t n_staged = 0u;
+        // Candidates are staged per LANE (entry k of lane l at stage[32 k + l]): a row's candidates then need no vote, prefix or
+        // shared cursor -- a lane that holds one stores it and bumps its own count -- and the warp-wide bookkeeping (one scan, one
+        // reservation in the frame's slot) happens once per flush, every dozen rows or so, instead of once per row.
+        uint32_t my_staged = 0u;   // this lane's staged keys
         auto flush_stage = [&]() {
             __syncwarp();
+            uint32_t incl = my_staged;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             uint32_t g = 0u;
-            if (lane == 0) g = atomicAdd(counter, n_staged);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            for (uint32_t i = lane; i < n_staged; i += 32)
-                if (g + i < p.cand_capacity) slot[g + i] = ws.stage[i];
+            if (lane == 0) g = atomicAdd(counter, total);
+            g = __shfl_sync(0xffffffffu, g, 0) + incl - my_staged;
+            for (uint32_t k = 0; k < my_staged; ++k)
+                if (g + k < p.cand_capacity) slot[g + k] = ws.stage[32u * k + uint32_t(lane)];
             __syncwarp();
-            n_staged = 0u;
+            my_staged = 0u;
         };
         float *resp_map = p.response_map ? p.response_map + int64_t(frame) * fv.rows * fv.cols : nullptr;
         // pre-existing features: the response is only evaluated where the mask is set (harris.cpp:94), 0 elsewhere
@@ -272,26 +283,19 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
                             if (v > big) mine |= 1u << j;
                         }
                         if (__any_sync(0xffffffffu, mine != 0u)) {
-                            // Stage slots: a lane owns up to four candidates, so its count has three bits and the warp's exclusive prefix is
-                            // three ballots (one vote + one popcount per bit) instead of a vote per column; only the lanes that hold a
-                            // candidate then run the stores.
-                            const uint32_t cnt = uint32_t(__popc(mine));
-                            const uint32_t lt = (1u << lane) - 1u;
-                            const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
                             if (mine != 0u) {
-                                uint32_t pos = n_staged + uint32_t(__popc(b0 & lt)) + 2u * uint32_t(__popc(b1 & lt)) + 4u * uint32_t(__popc(b2 & lt));
                                 const uint32_t lo0 = (uint32_t(m + p.tile.row_offset) << 16) | uint32_t(c0);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     if ((mine >> j) & 1u) {
                                         const uint32_t b = __float_as_uint(resp[p2][j]);
                                         const uint32_t hi = b ^ ~(uint32_t(int32_t(b) >> 31) | 0x80000000u);   // ~float_to_ordered(b)
-                                        stage2[pos++] = make_uint2(lo0 + uint32_t(j), hi);
+                                        stage2[32u * my_staged + uint32_t(lane)] = make_uint2(lo0 + uint32_t(j), hi);
+                                        ++my_staged;
                                     }
                                 }
                             }
-                            n_staged += uint32_t(__popc(b0)) + 2u * uint32_t(__popc(b1)) + 4u * uint32_t(__popc(b2));
-                            if (n_staged > CT_STAGE - 128) flush_stage();
+                            if (__any_sync(0xffffffffu, my_staged > uint32_t(CT_LANE_SLOTS - 4))) flush_stage();
                         }
                     }
 #pragma unroll
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(CORNER_TMA_THREADS, 1) corner_tma_kernel(const
             }
             s_cur = s_next;
         }
-        if (n_staged != 0u) flush_stage();
+        if (__any_sync(0xffffffffu, my_staged != 0u)) flush_stage();
         __syncwarp();
     }
 }
