@@ -232,18 +232,33 @@ __global__ void __launch_bounds__(FAST_SPARSE_THREADS, 1) fast_sparse_kernel(con
                     while (k_lo >= segs[sg + 1].k_start) ++sg;
                 uint32_t mine = 0u;
                 float resp[4];
+                // The word's four pixels have consecutive indices, and a segment of the offset table spans thousands: unless a
+                // boundary falls inside the word (or a mask thins the indices out) the four offsets are one base and one step.
+                const bool one_seg = !MASKED && able != 0u && k_row + uint32_t(c0) < segs[sg + 1].k_start;   // pixel j = 3 is the word's last
+                if (one_seg) {
+                    const uint32_t step = segs[sg].step;
+                    const uint32_t bits0 = segs[sg].bits_start + (k_row + uint32_t(c0 - 3) - segs[sg].k_start) * step;   // (never used for a j left of the interior)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    resp[j] = 0.0f;
-                    if ((able >> (8 * j + 7)) & 1u) {
-                        const uint32_t k = MASKED ? k_lo + __popc(mword & m_interior & ((1u << ((c0 & 31) + j)) - 1u)) : k_row + uint32_t(c0 + j - 3);
-                        int sj = sg;
-                        while (k >= segs[sj + 1].k_start) ++sj;
-                        const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
-                        const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);   // fast.cpp:89, one rounding
-                        if (v > p.thr) {                                                    // fast.cpp:90
-                            resp[j] = v;
-                            mine |= 1u << j;
+                    for (int j = 0; j < 4; ++j) {
+                        const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), __uint_as_float(bits0 + uint32_t(j) * step));   // fast.cpp:89, one rounding
+                        const bool pass = ((able >> (8 * j + 7)) & 1u) && v > p.thr;                                               // fast.cpp:90
+                        resp[j] = pass ? v : 0.0f;
+                        mine |= pass ? (1u << j) : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        resp[j] = 0.0f;
+                        if ((able >> (8 * j + 7)) & 1u) {
+                            const uint32_t k = MASKED ? k_lo + __popc(mword & m_interior & ((1u << ((c0 & 31) + j)) - 1u)) : k_row + uint32_t(c0 + j - 3);
+                            int sj = sg;
+                            while (k >= segs[sj + 1].k_start) ++sj;
+                            const float off = __uint_as_float(segs[sj].bits_start + (k - segs[sj].k_start) * segs[sj].step);
+                            const float v = __fadd_rn(float((sp >> (8 * j)) & 0xFFu), off);   // fast.cpp:89, one rounding
+                            if (v > p.thr) {                                                    // fast.cpp:90
+                                resp[j] = v;
+                                mine |= 1u << j;
+                            }
                         }
                     }
                 }
