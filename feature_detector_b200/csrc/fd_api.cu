@@ -482,26 +482,28 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             a.inv_cnt = inv;
             a.inv_cnt2 = inv2;
             {
-                // harris.cpp:98: (trace * trace * 0.21f * inv_cnt2) > thr, i.e. fl(fl(tt * 0.21f) * inv2) > thr -- two roundings of a
-                // non-negative tt, monotone non-decreasing in tt, so the set of passing tt is an upper interval of the floats.  Its
-                // lower end is found by bisection over the bit patterns of the non-negative floats (which order like the floats).
+                // harris.cpp:98: (trace * trace * 0.21f * inv_cnt2) > thr, i.e. fl(fl(fl(trace * trace) * 0.21f) * inv2) > thr -- three
+                // roundings of a non-negative trace (a sum of squares), each monotone non-decreasing, so the passing traces are an upper
+                // interval of the floats.  Its lower end is found by bisection over the bit patterns of the non-negative floats (which
+                // order like the floats).
                 auto passes = [&](uint32_t bits) {
-                    float tt;
-                    std::memcpy(&tt, &bits, 4);
-                    volatile float t1 = tt * 0.21f;
+                    float trace;
+                    std::memcpy(&trace, &bits, 4);
+                    volatile float t0 = trace * trace;
+                    volatile float t1 = t0 * 0.21f;
                     volatile float t2 = t1 * inv2;
                     return t2 > a.thr;
                 };
                 uint32_t lo = 0u, hi = 0x7F800000u;   // +0 .. +inf
                 if (!passes(hi)) {
-                    a.harris_tt_min = std::nanf("");   // no tt passes (thr is +inf or NaN): tt >= NaN is false
+                    a.harris_trace_min = std::nanf("");   // no trace passes (thr is +inf or NaN): trace >= NaN is false
                 } else {
                     while (lo < hi) {
                         const uint32_t mid = lo + (hi - lo) / 2;
                         if (passes(mid)) hi = mid;
                         else lo = mid + 1;
                     }
-                    std::memcpy(&a.harris_tt_min, &lo, 4);
+                    std::memcpy(&a.harris_trace_min, &lo, 4);
                 }
             }
             a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);

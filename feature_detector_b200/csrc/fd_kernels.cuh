@@ -80,7 +80,7 @@ struct CornerArgs {
     float thr;                // kMinValidResponse
     float alpha;              // Harris kAlpha
     float inv_cnt, inv_cnt2;  // 1/9 and its square, rounded as the reference rounds them (harris.cpp:71-72)
-    float harris_tt_min;      // Harris: the smallest trace^2 that passes the pre-test of harris.cpp:98 (NaN: none does); see fd_api.cu
+    float harris_trace_min;   // Harris: the smallest trace that passes the pre-test of harris.cpp:98 (NaN: none does); see fd_api.cu
     uint64_t *cand_keys;
     uint32_t *cand_counts;
     uint32_t cand_capacity;
