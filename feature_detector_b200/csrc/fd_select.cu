@@ -13,7 +13,7 @@
 // select_kernel: one CTA per frame, no global sort.  Frame pixels are binned into a grid of (d+1)-sided
 // cells; two kept points can never share a cell, and anything within d of a pixel lies in the 3x3 cells
 // around it.  Rounds until no candidate is alive, in one of two forms with identical results:
-//   per candidate (select_kernel<false>, frames of up to SELECT_CELLS_MIN candidates)
+//   per candidate (select_kernel<false, .>, frames of up to SELECT_CELLS_MIN candidates)
 //     A  every live candidate within d of a point kept in the previous round dies; the others post their key
 //        to their cell with a shared-memory 64-bit atomicMin and move to the next round's key list;
 //     B  a live candidate that holds its cell's minimum and beats the minima of the 8 neighbouring cells has no
@@ -22,7 +22,7 @@
 //     Work per round is proportional to the candidates still alive, and the first round kills most of them.  While live
 //     candidates outnumber cells (the first rounds) step B is one pass over the cell grid in shared memory -- the cells'
 //     minima ARE the candidates that can win -- instead of a second pass over the live list in global memory.
-//   per cell (select_kernel<true>, frames with more candidates: FAST at the reference's default threshold, 4K Harris)
+//   per cell (select_kernel<true, .>, frames with more candidates: FAST at the reference's default threshold, 4K Harris)
 //     the admitted candidates are grouped by cell once; a cell whose best live candidate beats the best of the 8 cells
 //     around it keeps it; cells next to a fresh point drop the candidates it covers and recompute their best.  The rounds
 //     walk the list of cells that hold candidates, not the grid.
@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(256) select_admit_kernel(const SelectArgs p) {
 
 // BY_CELLS picks the form of the rounds; a launch of one form leaves the frames of the other alone (the candidate counts live
 // on the device, so the host launches both forms whenever the capacity admits the per-cell one).
-template <bool BY_CELLS>
+// CELLS_SMEM: the per-cell state lives in shared memory (the usual case) -- a template parameter rather than a run-time choice so that
+// its accesses compile to LDS / STS / ATOMS with 32-bit addresses instead of generic loads behind 64-bit address arithmetic.
+template <bool BY_CELLS, bool CELLS_SMEM>
 __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_kernel(const SelectArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int frame = blockIdx.x;
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_k
     const int n_cells = pitch * (p.cells_y + 2);
     // per-cell state, shared (or, for very fine grids, global): the best live key of the cell's candidates, the point kept in
     // the cell, where the cell's candidates start in the binned list, and the round in which the cell's point was kept
-    uint8_t *cell_base = p.cells_in_smem ? smem : reinterpret_cast<uint8_t *>(p.cell_scratch) + int64_t(frame) * p.cell_stride;
+    uint8_t *cell_base = CELLS_SMEM ? smem : reinterpret_cast<uint8_t *>(p.cell_scratch) + int64_t(frame) * p.cell_stride;
     unsigned long long *cmin = reinterpret_cast<unsigned long long *>(cell_base);
     uint32_t *cells = reinterpret_cast<uint32_t *>(cmin + n_cells);
     uint32_t *cstart = cells + n_cells;                                 // n_cells + 1 entries
@@ -652,13 +654,17 @@ cudaError_t launch_select(const SelectArgs &args, cudaStream_t stream) {
     // one CTA per frame: with fewer frames than SMs (the drop-in classes' one frame per call) a CTA has its SM to itself, and the
     // passes that stream over a frame's candidates are what its latency is made of
     const int threads = (args.cells_in_smem && args.n_frames > 148) ? SELECT_THREADS : SELECT_MAX_THREADS;
-    cudaError_t e = cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    select_kernel<false><<<args.n_frames, threads, smem, stream>>>(args);
-    if (args.cand_capacity > args.cells_min) {   // some frame may hold enough candidates for the per-cell form
-        e = cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    auto launch = [&](auto kernel) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
-        select_kernel<true><<<args.n_frames, threads, smem, stream>>>(args);
+        kernel<<<args.n_frames, threads, smem, stream>>>(args);
+        return cudaSuccess;
+    };
+    cudaError_t e = args.cells_in_smem ? launch(select_kernel<false, true>) : launch(select_kernel<false, false>);
+    if (e != cudaSuccess) return e;
+    if (args.cand_capacity > args.cells_min) {   // some frame may hold enough candidates for the per-cell form
+        e = args.cells_in_smem ? launch(select_kernel<true, true>) : launch(select_kernel<true, false>);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
