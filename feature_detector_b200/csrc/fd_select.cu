@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(256) select_admit_kernel(const SelectArgs p) {
 // CELLS_SMEM: the per-cell state lives in shared memory (the usual case) -- a template parameter rather than a run-time choice so that
 // its accesses compile to LDS / STS / ATOMS with 32-bit addresses instead of generic loads behind 64-bit address arithmetic.
 template <bool BY_CELLS, bool CELLS_SMEM>
-__global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : 2) select_kernel(const SelectArgs p) {
+#ifndef FD_SELECT_MINBLOCKS
+#define FD_SELECT_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(SELECT_MAX_THREADS, BY_CELLS ? 1 : FD_SELECT_MINBLOCKS) select_kernel(const SelectArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int frame = blockIdx.x;
     const int d = p.min_distance;
