@@ -21,3 +21,9 @@ for f in feature_detector_b200/csrc/fd_*.cu; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -fmad=false -Xptxas -v -c -o /dev/null $f 2>&1 |
     grep -E "Compiling entry|registers|spill" | sed -E "s/ptxas info    : //; s/Compiling entry function '([^']*)' for 'sm_100a'/\1/" | paste - - - | c++filt | sed 's/fdb::(anonymous namespace):://g' | cut -c1-260
 done
+echo
+echo "## generic (unspecialised address space) loads / stores / atomics per object: LD.E / ST.E / ATOM.E in the SASS"
+echo "## (fd_select: one LD.E.64 per instantiation, the kept list read from shared or from global memory in the final ordering)"
+for f in feature_detector_b200/csrc/fd_*.o; do
+  echo "$(basename $f .o): LD $(cuobjdump -sass $f | grep -c ' LD\.E') ST $(cuobjdump -sass $f | grep -c ' ST\.E') ATOM $(cuobjdump -sass $f | grep -c ' ATOM\.E')"
+done
