@@ -82,6 +82,7 @@ struct fd_context {
     int items_per_warp = 8;    // FD_B200_ITEMS_PER_WARP: tuning knob, work items each resident warp should get (band height follows)
     uint32_t select_cells_min = SELECT_CELLS_MIN;   // FD_B200_SELECT_CELLS_MIN: testing knob, candidate count above which selection runs its rounds per cell
     bool force_dense_fast = false;  // FD_B200_FAST_DENSE=1: testing knob, always take the dense kernel
+    int select_smem_kb = 200;       // FD_B200_SELECT_SMEM_KB: testing knob, the most shared memory a frame's cell state may take when a CTA has its SM to itself
     bool select_prepare = true;     // FD_B200_SELECT_PREPARE=0: testing knob, selection always builds its rank histogram and first range itself
 
     void *host_stage = nullptr;     // pinned staging block of fd_detect_describe_host
@@ -568,7 +569,9 @@ fd_status run_select(fd_context *ctx, const fd_detect_params *p, int rows, int c
     const size_t cell_bytes = select_cell_bytes(a.cells_x, a.cells_y);   // the grid carries a one-cell empty border
     // ceil(2^32 / cell) does not fit 32 bits for cells of one pixel (min distance 0): 0 stands for the identity there
     a.cell_magic = cell == 1 ? 0u : uint32_t(((uint64_t(1) << 32) + cell - 1) / uint64_t(cell));
-    a.cells_in_smem = cell_bytes <= 48 * 1024;
+    // The per-cell state lives in shared memory when it fits beside three other frames' CTAs on the SM -- or, with no more frames than
+    // SMs (a CTA has its SM to itself), whenever it fits at all: a 1920x1080 frame at d = 20 has 5 000 cells, 100 KB.
+    a.cells_in_smem = cell_bytes <= size_t(fv.n_frames <= ctx->sm_count ? ctx->select_smem_kb : 48) * 1024;
     if (!a.cells_in_smem) {
         FD_TRY(reserve(ctx, ctx->cells, cell_bytes * fv.n_frames));
         a.cell_scratch = static_cast<uint32_t *>(ctx->cells.ptr);
@@ -650,6 +653,7 @@ fd_status fd_create(int device_ordinal, fd_context **out_ctx) {
     if (const char *env = std::getenv("FD_B200_CORNER_STREAM")) ctx->force_stream_corner = (env[0] == '1');
     if (const char *env = std::getenv("FD_B200_ITEMS_PER_WARP")) ctx->items_per_warp = std::max(1, atoi(env));
     if (const char *env = std::getenv("FD_B200_SELECT_PREPARE")) ctx->select_prepare = (env[0] != '0');
+    if (const char *env = std::getenv("FD_B200_SELECT_SMEM_KB")) ctx->select_smem_kb = std::max(0, std::min(200, std::atoi(env)));
     if (const char *env = std::getenv("FD_B200_SELECT_CELLS_MIN")) ctx->select_cells_min = uint32_t(std::strtoul(env, nullptr, 10));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
