@@ -19,7 +19,8 @@ namespace {
 
 constexpr int NN_STEPS = 2;                 // 128-column steps per pass over a row: 256 columns, one float4 per lane per step
 constexpr int NN_CHUNK_ROWS = 16;            // rows per work item
-constexpr int NN_STAGE = 128 * NN_STEPS;    // candidate keys staged per warp between slot reservations: one pass always fits
+constexpr int NN_LANE_SLOTS = 16;           // candidate keys each lane can stage between flushes (a pass adds at most 4 * NN_STEPS)
+constexpr int NN_STAGE = 32 * NN_LANE_SLOTS; // ... per warp: entry k of lane l sits at stage[32 k + l]
 
 // One warp per run of consecutive valid rows (the invalid boundary rows are never read).  Per pass the warp issues all its
 // float4 loads, reduces every element to one bit (above the threshold, inside the column bounds), and only then do the lanes
@@ -27,9 +28,7 @@ constexpr int NN_STAGE = 128 * NN_STEPS;    // candidate keys staged per warp be
 // write their keys.  The stage leaves for the frame's candidate slot in blocks: one reservation, one coalesced copy.
 __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) {
     __shared__ uint64_t stage_all[8][NN_STAGE];
-    __shared__ uint32_t fill_all[8];
     uint64_t *stage = stage_all[threadIdx.x >> 5];
-    uint32_t *fill = fill_all + (threadIdx.x >> 5);   // next free stage slot (the lanes' atomic cursor)
     const int lane = lane_id();
     const int b = p.invalid_boundary;
     const int valid_rows = p.rows - 2 * b;
@@ -38,24 +37,29 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
     const int64_t map_px = int64_t(p.rows) * p.cols;
     const bool vec = (p.cols % 4 == 0) && (reinterpret_cast<uintptr_t>(p.heatmap) % 16 == 0);
     const int col_lo = b, col_hi = p.cols - b;   // valid columns: col_lo <= col < col_hi
-    if (lane == 0) *fill = 0u;
-    __syncwarp();
     int frame = 0, row = 0;
-    uint32_t staged = 0u;   // keys in the stage (warp-uniform copy of *fill)
+    // Candidates are staged per LANE (as in fd_corner_tma.cu): a lane that finds one stores it and bumps its own count; the warp-wide
+    // scan and the reservation in the frame's slot happen once per flush.
+    uint32_t my_staged = 0u;   // this lane's staged keys
     auto flush = [&]() {
         __syncwarp();
-        if (staged != 0u) {
-            uint32_t base = 0u;
-            if (lane == 0) base = atomicAdd(p.cand_counts + frame, staged);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
-            for (uint32_t i = lane; i < staged; i += 32)
-                if (base + i < p.cand_capacity) slot[base + i] = stage[i];
-            __syncwarp();
-            if (lane == 0) *fill = 0u;
-            __syncwarp();
-            staged = 0u;
+        uint32_t incl = my_staged;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total != 0u) {
+            uint32_t g = 0u;
+            if (lane == 0) g = atomicAdd(p.cand_counts + frame, total);
+            g = __shfl_sync(0xffffffffu, g, 0) + incl - my_staged;
+            uint64_t *slot = p.cand_keys + int64_t(frame) * p.cand_capacity;
+            for (uint32_t k = 0; k < my_staged; ++k)
+                if (g + k < p.cand_capacity) slot[g + k] = stage[32u * k + uint32_t(lane)];
+        }
+        __syncwarp();
+        my_staged = 0u;
     };
     // runs of NN_CHUNK_ROWS consecutive valid rows are handed out by a global counter (zeroed by the host): the cost of a run
     // follows its candidate count, so a fixed partition leaves a tail
@@ -98,11 +102,8 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
                 }
                 mine |= m << (4 * k);
             }
-            const uint32_t added = __reduce_add_sync(0xffffffffu, uint32_t(__popc(mine)));
-            if (added != 0u) {
-                if (staged + added > uint32_t(NN_STAGE)) flush();
+            if (__any_sync(0xffffffffu, mine != 0u)) {
                 if (mine != 0u) {
-                    uint32_t at = atomicAdd(fill, uint32_t(__popc(mine)));
                     do {
                         const int bit = __ffs(mine) - 1;
                         mine &= mine - 1u;
@@ -111,10 +112,11 @@ __global__ void __launch_bounds__(256) nn_heatmap_kernel(const NnHeatmapArgs p) 
                         static_assert(NN_STEPS == 2, "the select tree below is written for two steps");
                         const float4 w = k ? q[1] : q[0];
                         const float v = (bit & 2) ? ((bit & 1) ? w.w : w.z) : ((bit & 1) ? w.y : w.x);
-                        stage[at++] = (uint64_t(~float_to_ordered(v)) << 32) | uint32_t(~((uint32_t(row) << 16) | uint32_t(c)));
+                        stage[32u * my_staged + uint32_t(lane)] = (uint64_t(~float_to_ordered(v)) << 32) | uint32_t(~((uint32_t(row) << 16) | uint32_t(c)));
+                        ++my_staged;
                     } while (mine != 0u);
                 }
-                staged += added;
+                if (__any_sync(0xffffffffu, my_staged > uint32_t(NN_LANE_SLOTS - 4 * NN_STEPS))) flush();
             }
         }
         if (++row == p.rows - b) {   // the run continues in the next frame
