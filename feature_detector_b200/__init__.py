@@ -151,6 +151,7 @@ def load_library():
         "fd_tiled_root_context": (vp, [vp]),
         "fd_debug_fast_offset_bits": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint32), i32p]),
         "fd_debug_run_length_lut": (C.c_int, [u8p]),
+        "fd_debug_harris_trace_min": (C.c_int, [C.c_float, C.POINTER(C.c_float)]),
         "fd_debug_check_guards": (C.c_int, [vp, i32p]),
     }
     for name, (res, args) in sig.items():

@@ -322,6 +322,34 @@ bool ensure_frame_map(fd_context *ctx, bool for_corner = false) {
     return true;
 }
 
+// harris.cpp:98 tests (trace * trace * 0.21f * inv_cnt2) > thr, i.e. fl(fl(fl(trace * trace) * 0.21f) * inv2) > thr with inv2 = fl(fl(1/9)^2)
+// (harris.cpp:71-72): three roundings of a non-negative trace (a sum of squares), each monotone non-decreasing, so the passing traces are
+// an upper interval of the floats.  Its lower end is found by bisection over the bit patterns of the non-negative floats (which order like
+// the floats); NaN when no trace passes (thr is +inf or NaN: trace >= NaN is false).
+float harris_trace_min(float thr) {
+    volatile float nine = 9.0f;
+    volatile float inv = 1.0f / nine;
+    volatile float inv2 = inv * inv;
+    auto passes = [&](uint32_t bits) {
+        float trace;
+        std::memcpy(&trace, &bits, 4);
+        volatile float t0 = trace * trace;
+        volatile float t1 = t0 * 0.21f;
+        volatile float t2 = t1 * inv2;
+        return t2 > thr;
+    };
+    uint32_t lo = 0u, hi = 0x7F800000u;   // +0 .. +inf
+    if (!passes(hi)) return std::nanf("");
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (passes(mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    float out;
+    std::memcpy(&out, &lo, 4);
+    return out;
+}
+
 // Split the interior rows into bands so that every resident warp gets several work items.
 void plan_bands(const fd_context *ctx, int interior_rows, int n_strips, int n_frames, int warps_per_cta, int ctas_per_sm, int min_band,
                 int band_multiple, int &band_rows, int &n_bands, int64_t &n_items, int &grid) {
@@ -482,31 +510,7 @@ fd_status run_candidates(fd_context *ctx, const fd_detect_params *p, int cand_ca
             volatile float inv2 = inv * inv;                  // harris.cpp:72
             a.inv_cnt = inv;
             a.inv_cnt2 = inv2;
-            {
-                // harris.cpp:98: (trace * trace * 0.21f * inv_cnt2) > thr, i.e. fl(fl(fl(trace * trace) * 0.21f) * inv2) > thr -- three
-                // roundings of a non-negative trace (a sum of squares), each monotone non-decreasing, so the passing traces are an upper
-                // interval of the floats.  Its lower end is found by bisection over the bit patterns of the non-negative floats (which
-                // order like the floats).
-                auto passes = [&](uint32_t bits) {
-                    float trace;
-                    std::memcpy(&trace, &bits, 4);
-                    volatile float t0 = trace * trace;
-                    volatile float t1 = t0 * 0.21f;
-                    volatile float t2 = t1 * inv2;
-                    return t2 > a.thr;
-                };
-                uint32_t lo = 0u, hi = 0x7F800000u;   // +0 .. +inf
-                if (!passes(hi)) {
-                    a.harris_trace_min = std::nanf("");   // no trace passes (thr is +inf or NaN): trace >= NaN is false
-                } else {
-                    while (lo < hi) {
-                        const uint32_t mid = lo + (hi - lo) / 2;
-                        if (passes(mid)) hi = mid;
-                        else lo = mid + 1;
-                    }
-                    std::memcpy(&a.harris_trace_min, &lo, 4);
-                }
-            }
+            a.harris_trace_min = harris_trace_min(a.thr);
             a.cand_keys = static_cast<uint64_t *>(ctx->keys.ptr);
             a.cand_counts = static_cast<uint32_t *>(ctx->counts.ptr);
             a.cand_capacity = cap;
@@ -1528,6 +1532,12 @@ fd_status fd_debug_fast_offset_bits(uint32_t count, uint32_t *out_bits, int32_t 
         while (k >= segs[s + 1].k_start) ++s;
         out_bits[k] = segs[s].bits_start + (k - segs[s].k_start) * segs[s].step;
     }
+    return FD_OK;
+}
+
+fd_status fd_debug_harris_trace_min(float min_valid_response, float *out_trace_min) {
+    if (!out_trace_min) return FD_ERR_INVALID_ARGUMENT;
+    *out_trace_min = harris_trace_min(min_valid_response);
     return FD_OK;
 }
 

@@ -307,6 +307,9 @@ fd_status fd_nn_sample_descriptors_at(fd_context *ctx, const float *dev_maps, in
 fd_status fd_debug_fast_offset_bits(uint32_t count, uint32_t *out_bits, int32_t *n_segments);
 /* The 65536-entry longest-circular-run table the FAST kernel looks scores up in. */
 fd_status fd_debug_run_length_lut(uint8_t *out_65536);
+/* The smallest trace (sum of the two windowed squared-gradient sums) that passes the Harris pre-test of harris.cpp:98 at this threshold --
+ * the kernel replaces the test's three multiplications by one compare against it; NaN when no trace passes. */
+fd_status fd_debug_harris_trace_min(float min_valid_response, float *out_trace_min);
 
 /* Memory-safety check that needs no external tool: a context created while the environment holds FD_B200_GUARD=1 allocates every
  * context-owned device buffer at exactly the size a call asks for, between two 256-byte red zones.  This call synchronises and

@@ -128,3 +128,32 @@ def test_sparse_fast_filter_is_conservative():
         assert flagged[a > diff].all(), diff                             # conservative: nothing above diff slips through
         if (diff + 1) & diff == 0:
             assert not flagged[a <= diff].any(), diff                    # exact for diff + 1 a power of two
+
+
+def test_harris_pretest_threshold_is_the_exact_boundary():
+    """The Harris kernel replaces the pre-test of feature_point_harris_detector.cpp:98, (trace * trace * 0.21f * inv_cnt2) > thr, by
+    one compare against the smallest trace that passes (bisected on the host).  For many thresholds: that float passes the float32
+    expression, the float just below it does not, and random traces agree with the expression."""
+    lib = fd.load_library()
+    inv = np.float32(1.0) / np.float32(9.0)
+    inv2 = np.float32(inv * inv)
+
+    def passes(trace, thr):
+        t = np.float32(np.float32(np.float32(trace) * np.float32(trace)) * np.float32(0.21))
+        return bool(np.float32(t * inv2) > np.float32(thr))
+
+    rng = np.random.default_rng(3)
+    thresholds = [0.0, 0.1, 1.0, 30.0, 1e3, 1e9, -1.0, 1e-30, 3.0e38] + rng.uniform(0, 500, 40).tolist() + (10 ** rng.uniform(-6, 12, 40)).tolist()
+    out = C.c_float(0)
+    with np.errstate(over="ignore"):
+        for thr in thresholds:
+            assert lib.fd_debug_harris_trace_min(C.c_float(thr), C.byref(out)) == 0
+            t_min = np.float32(out.value)
+            assert passes(t_min, thr), thr
+            if t_min > 0:
+                below = np.nextafter(t_min, np.float32(-1), dtype=np.float32)
+                assert not passes(below, thr), thr
+            for trace in (rng.uniform(0, 2, 50) * float(t_min) if np.isfinite(t_min) and t_min > 0 else rng.uniform(0, 1e6, 50)):
+                assert passes(np.float32(trace), thr) == bool(np.float32(trace) >= t_min), (thr, trace)
+        for thr in (float("inf"), float("nan")):        # nothing passes: the kernel's compare against NaN is false for every trace
+            assert lib.fd_debug_harris_trace_min(C.c_float(thr), C.byref(out)) == 0 and np.isnan(out.value)
