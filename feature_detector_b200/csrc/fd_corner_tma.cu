@@ -14,6 +14,11 @@
 //     conversion is left before the response;
 //   * the row loop is unrolled over one TMA group (12 rows = 4 turns of the 3-slot register pipeline), so every shared-
 //     memory address is a group base plus a compile-time offset.
+//   * that exactness is used throughout: neighbouring 3-sums share a pair sum, products that feed one sum ride on an FMA, the
+//     column-validity test is the response threshold (+inf outside the interior), threshold and strip ownership are a fifth operand of
+//     the 4-neighbour maximum, and the Harris pre-test is one compare of the trace against a threshold bisected on the host;
+//   * candidates are staged per lane (entry k of lane l at stage[32 k + l]): no vote, prefix or shared cursor per row, one scan and
+//     one reservation in the frame's slot per flush.
 // Used when the frames can be described by a tensor map (with or without a pre-existing-feature mask).
 #include <cuda.h>
 
