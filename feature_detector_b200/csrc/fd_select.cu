@@ -30,7 +30,8 @@
 // select_hist_kernel / select_admit_kernel: few frames with many candidates each (a batch of 3840x2160 frames, the gathered
 // tiles of one) would leave most SMs idle while each frame's one CTA streams over all of its keys twice; these two kernels
 // build the histogram and compact the first rank range with many CTAs per frame, and select_kernel starts from their output.
-// The kept list is then sorted by key (a few hundred entries, bitonic in shared memory) and cut at
+// The kept list is then ordered by key (a few hundred entries: bitonic in shared memory, or -- few frames, where latency counts -- by
+// counting smaller keys, one barrier instead of dozens) and cut at
 // max(needed - existing, 1) -- the reference tests the count AFTER each push (:67-68), so needed = 0 still
 // yields one feature.  Pre-existing features need no handling here: their squares were already masked out of
 // candidate generation with the same d (feature_point_detector.cpp:12-16); they only count toward `needed`.
